@@ -1,0 +1,145 @@
+// difacto_b200/csrc/dfb_internal.cuh -- shared declarations of the sm_100a engine.
+//
+// Data layout in HBM (one shard = one GPU):
+//   Entry tab[cap]        32-byte open-addressing hash entries, one DRAM sector each:
+//                         {u64 reversed key, i32 vrow, i32 pad, f32 fea_cnt, w, sqrt_g, z}
+//                         == the reference's unordered_map<feaid_t,SGDEntry> (sgd_updater.h:19-29,84)
+//   float V  [vcap][ks]   embedding rows, ks = V_dim rounded up to 4 floats (16-byte rows)
+//   float Vcg[vcap][ks]   AdaGrad accumulators (the second half of SGDEntry::V, sgd_updater.cc:142)
+// V rows are allocated lazily from a bump pool, exactly when the reference calls InitV.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dfb {
+
+struct __align__(32) Entry {
+  unsigned long long key;
+  int vrow;       // -1: no V allocated (SGDEntry::V == nullptr)
+  int pad;
+  float fea_cnt, w, sqrt_g, z;
+};
+static_assert(sizeof(Entry) == 32, "Entry must be one 32-byte sector");
+
+constexpr unsigned long long kEmptyKey = ~0ULL;  // ReverseBytes(id % (2^64-1)) never yields it
+
+// SGDUpdaterParam (src/sgd/sgd_param.h:66-107)
+struct Params {
+  float l1, l2, V_l2, lr, lr_beta, V_lr, V_lr_beta, V_init_scale;
+  int V_dim, V_threshold;
+  unsigned seed;
+};
+
+// accumulated on device, read back by dfb_read_progress
+struct DevProgress {
+  double loss, penalty, auc;
+  unsigned long long nrows, new_keys, new_vrows;
+  int err;        // sticky dfb_status raised by a kernel (capacity, invalid lens ...)
+  int pad;
+};
+
+// device-resident mutable scalars of the table
+struct TableState {
+  unsigned long long n_keys;
+  unsigned long long n_vrows;
+  unsigned int seed;     // SGDUpdaterParam::seed as advanced by rand_r (sgd_updater.cc:144)
+  unsigned int pad;
+};
+
+struct Table {
+  Entry* tab = nullptr;
+  uint64_t cap = 0, mask = 0, max_keys = 0;
+  float* V = nullptr;
+  float* Vcg = nullptr;
+  uint64_t vcap = 0;
+  int ks = 0;  // row stride in floats
+  TableState* state = nullptr;
+  DevProgress* prog = nullptr;
+};
+
+// how a kernel finds w / V (and where it puts the gradient) for local key u of a batch
+struct FmView {
+  // w = wbase[w_pos ? w_pos[u] : u]; w_pos[u] == -1 -> 0
+  const float* wbase;
+  const int* w_pos;
+  // V row = vbase + (int64)r * vstride, r = v_pos[u] (or u when dense && v_pos[u] >= 0); -1 -> absent
+  const float* vbase;
+  const int* v_pos;
+  long long vstride;
+  int dense;
+  // gradient destinations (TRAIN): gw[gw_pos ? gw_pos[u] : u], gV row = gvbase + r' * gvstride with
+  // r' = (gv_pos ? gv_pos[u] : u); gxxp[u] (only when values are present)
+  float* gwbase;
+  const int* gw_pos;
+  float* gvbase;
+  const int* gv_pos;
+  long long gvstride;
+  float* gxxp;
+};
+
+struct FmBatch {
+  size_t nrows;
+  const uint64_t* offset;   // size_t offsets, as in dmlc::RowBlock (dmlc/data.h:141)
+  const uint32_t* index;
+  const float* value;       // nullptr: binary features
+  const float* label;
+  const float* pred_in;     // CalcGrad with a caller-provided pred (fm_loss.h:155-161), else nullptr
+  float* pred_io;           // output; accumulated into when pred_acc
+  int pred_acc;
+  int V_dim;
+  int train;
+  DevProgress* prog;        // loss / nrows accumulated here when non-null
+};
+
+// ---- launchers (kernels_fm.cu) ----
+// returns number of kernel launches performed, or <0 on invalid configuration
+int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t s);
+int launch_grad_finalize(int V_dim, size_t nkeys, const float* weights, const int* V_pos,
+                         const float* xxp, float* grad, cudaStream_t s);
+
+// ---- launchers (kernels_table.cu) ----
+int launch_table_init(Table& t, unsigned seed, cudaStream_t s);
+// find (or insert) keys; slot_out[i] = hash position or -1.  When pull outputs are non-null also
+// emits w and vrow of each entry.
+int launch_lookup(Table& t, const uint64_t* keys, size_t n, bool insert, int* slot_out,
+                  float* w_out, int* vrow_out, cudaStream_t s);
+// SGDUpdater::Update(kFeaCount) incl. the InitV pass.  flags/pos/cub_tmp are workspaces of n ints.
+int launch_feacnt(Table& t, const Params& p, const int* slot, size_t n, const float* cnt,
+                  int* flags, int* pos, void* cub_tmp, size_t cub_bytes, cudaStream_t s);
+size_t scan_tmp_bytes(size_t n);
+size_t sort_tmp_bytes(size_t n);
+// InitV for flagged keys, consuming the rand_r stream in key order (sgd_updater.cc:140-147)
+int launch_initv(Table& t, const Params& p, const int* slot, size_t n, int* flags, int* pos,
+                 void* cub_tmp, size_t cub_bytes, cudaStream_t s);
+// SGDUpdater::Get packing: lens -> scan -> ragged [w, V...] (sgd_updater.cc:32-56)
+int launch_pack_ragged(Table& t, const Params& p, const int* slot, size_t n, int* lens, int* pos,
+                       float* vals, unsigned long long* nvals_out, void* cub_tmp, size_t cub_bytes,
+                       cudaStream_t s);
+// dense rows for the sharded store: w[n], hasv[n] (-1/1), V[n][ks]
+int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* hasv_out,
+                       float* V_out, cudaStream_t s);
+// FTRL/AdaGrad from per-key dense gradient rows (fused path and sharded push).
+//   pull_vrow[i] >= 0 <=> the worker saw a V row at pull time (lens[i] > 1); when
+//   vrow_is_flag the actual row is taken from the entry.  gxxp == nullptr -> use gw (binary data).
+int launch_update_dense(Table& t, const Params& p, const int* slot, const int* pull_vrow,
+                        int vrow_is_flag, size_t n, const float* gw, const float* gxxp,
+                        const float* gV, int* flags, int accumulate_penalty, cudaStream_t s);
+// FTRL/AdaGrad from the reference's ragged gradient layout (sgd_updater.cc:74-98)
+int launch_update_ragged(Table& t, const Params& p, const int* slot, size_t n, const float* grads,
+                         const int* lens_or_null, const int* pos, int* flags, cudaStream_t s);
+// penalty over a pulled view without updating (validation batches, sharded worker)
+int launch_penalty(const Params& p, DevProgress* prog, const float* w_arr, const int* vrow,
+                   const float* V, int ks, int dense, size_t n, cudaStream_t s);
+int launch_pull_view(Table& t, const int* slot, size_t n, float* w_out, int* vrow_out,
+                     cudaStream_t s);
+int launch_lens_scan(const int* lens, size_t n, int* pos, void* cub_tmp, size_t cub_bytes,
+                     cudaStream_t s);
+// Loss::Evaluate / BinClassMetric::AUC on device; results added to prog (or written to out)
+int launch_evaluate(const float* label, const float* pred, size_t n, double* out, cudaStream_t s);
+int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp, float* val_tmp,
+               float* key_tmp2, float* val_tmp2, void* cub_tmp, size_t cub_bytes, double* out_add,
+               cudaStream_t s);
+int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* hasv, float* V,
+                        float* cg, int k, cudaStream_t s);
+
+}  // namespace dfb

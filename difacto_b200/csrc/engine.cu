@@ -1,0 +1,858 @@
+// difacto_b200/csrc/engine.cu -- host side of the engine and the C-ABI of include/difacto_b200.h.
+//
+// One engine = one shard of the model on one GPU + the workspaces of a minibatch.
+// (A) the API-faithful entry points move host buffers in and out around single kernels;
+// (B) dfb_train_step* is the fused device-resident minibatch of SGDLearner::IterateData
+//     (src/sgd/sgd_learner.cc:138-177 of the reference).
+#include <cuda_runtime.h>
+
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/difacto_b200.h"
+#include "dfb_internal.cuh"
+
+using namespace dfb;  // NOLINT
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct dfb_engine {
+  Params prm;
+  int device = 0;
+  int compute_auc = 1;
+  int force_generic = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  Table tab;
+  std::string err;
+  std::vector<std::pair<std::string, std::string>> unknown;
+  uint64_t launches = 0;
+
+  // workspaces (grown on demand)
+  DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
+  DevBuf auc_k, auc_v;
+  DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
+  DevBuf scal, hasv, rV, rcg, nvals;
+  // double-buffered inputs of the pipelined step
+  struct InSet { DevBuf off, idx, val, lab, keys, cnt; cudaEvent_t copied = nullptr, consumed = nullptr; } in[2];
+  uint64_t seq = 0;
+  DevProgress* h_prog = nullptr;   // pinned
+  unsigned long long* h_nvals = nullptr;  // pinned
+
+  int fail(int code, const std::string& msg) { err = msg; return code; }
+  int cuda_fail(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return DFB_ERR_CUDA;
+  }
+  // grow a workspace; frees/reallocs only after the compute stream has drained
+  int ensure(DevBuf& b, size_t bytes) {
+    if (bytes <= b.bytes && b.p) return 0;
+    if (bytes == 0) bytes = 16;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e;
+    if (b.p) {
+      if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sync");
+      if ((e = cudaStreamSynchronize(copy_stream)) != cudaSuccess) return cuda_fail(e, "sync");
+      cudaFree(b.p);
+      b.p = nullptr; b.bytes = 0;
+    }
+    if ((e = cudaMalloc(&b.p, want)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+    b.bytes = want;
+    return 0;
+  }
+};
+
+namespace {
+
+#define DFB_CUDA(h, call)                                                  \
+  do {                                                                     \
+    cudaError_t _e = (call);                                               \
+    if (_e != cudaSuccess) return (h)->cuda_fail(_e, #call);               \
+  } while (0)
+#define DFB_TRY(expr)              \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != 0) return _rc;      \
+  } while (0)
+
+uint64_t next_pow2(uint64_t x) {
+  uint64_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+bool parse_float(const std::string& s, float* out) {
+  if (s.empty()) return false;
+  char* end = nullptr;
+  errno = 0;
+  float v = strtof(s.c_str(), &end);
+  if (end == s.c_str() || *end != '\0') return false;
+  *out = v;
+  return true;
+}
+bool parse_i64(const std::string& s, long long* out) {
+  if (s.empty()) return false;
+  char* end = nullptr;
+  errno = 0;
+  long long v = strtoll(s.c_str(), &end, 10);
+  if (end == s.c_str() || *end != '\0') return false;
+  *out = v;
+  return true;
+}
+
+// check the sticky device error flag after a synchronisation point
+int check_dev_err(dfb_engine* h) {
+  int code = h->h_prog->err;
+  if (code == 0) return 0;
+  switch (code) {
+    case DFB_ERR_CAPACITY:
+      return h->fail(code, "table_capacity / V_capacity exhausted (raise table_capacity or V_capacity)");
+    case DFB_ERR_INVALID:
+      return h->fail(code, "invalid input detected on device (a CHECK of the reference would have failed: "
+                           "lens[i] != V_dim+1, gradient for a key without V, or key == UINT64_MAX)");
+    default:
+      return h->fail(code, "device-side error");
+  }
+}
+
+// D2H of the progress block, clearing the device accumulators (err is sticky until read)
+int fetch_progress(dfb_engine* h, dfb_progress* out) {
+  DFB_CUDA(h, cudaMemcpyAsync(h->h_prog, h->tab.prog, sizeof(DevProgress), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(h, cudaMemsetAsync(h->tab.prog, 0, sizeof(DevProgress), h->stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (out) {
+    out->loss = (float)h->h_prog->loss;
+    out->penalty = (float)h->h_prog->penalty;
+    out->auc = (float)h->h_prog->auc;
+    out->nnz_w = 0.f;
+    out->nrows = (float)h->h_prog->nrows;
+    out->new_keys = h->h_prog->new_keys;
+    out->new_vrows = h->h_prog->new_vrows;
+  }
+  return check_dev_err(h);
+}
+
+// synchronise and surface a device-side error without disturbing the accumulated Progress
+int sync_and_check(dfb_engine* h) {
+  DFB_CUDA(h, cudaMemcpyAsync(h->h_prog, h->tab.prog, sizeof(DevProgress), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->h_prog->err != 0) {
+    DFB_CUDA(h, cudaMemsetAsync(&h->tab.prog->err, 0, sizeof(int), h->stream));
+    DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return check_dev_err(h);
+}
+
+// read the scratch accumulator block (prog[1]) used by dfb_evaluate / dfb_auc
+int fetch_scratch(dfb_engine* h, DevProgress* out) {
+  DFB_CUDA(h, cudaMemcpyAsync(h->h_prog, h->tab.prog + 1, sizeof(DevProgress), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  *out = *h->h_prog;
+  return 0;
+}
+
+int ensure_key_ws(dfb_engine* h, size_t n) {
+  DFB_TRY(h->ensure(h->slot, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->u_w, n * sizeof(float)));
+  DFB_TRY(h->ensure(h->u_vrow, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->flags, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->pos, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->cub, scan_tmp_bytes(n)));
+  return 0;
+}
+
+int h2d(dfb_engine* h, DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
+  DFB_TRY(h->ensure(b, bytes));
+  if (bytes) DFB_CUDA(h, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+// the fused minibatch on device-resident inputs (everything enqueued on h->stream)
+int step_dev(dfb_engine* h, size_t nrows, const uint64_t* d_off, const uint32_t* d_idx, const float* d_val,
+             const float* d_lab, const uint64_t* d_keys, size_t U, const float* d_cnt, int is_train) {
+  if (U > 0x7fffffffULL || nrows > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "batch too large");
+  const int ks = h->tab.ks;
+  cudaStream_t s = h->stream;
+  DFB_TRY(ensure_key_ws(h, U));
+  DFB_TRY(h->ensure(h->pred, nrows * sizeof(float)));
+  int* slot = h->slot.as<int>();
+  float* u_w = h->u_w.as<float>();
+  int* u_vrow = h->u_vrow.as<int>();
+  int* flags = h->flags.as<int>();
+  int* pos = h->pos.as<int>();
+  // Push(kFeaCount) then Pull (sgd_learner.cc:214-217, :177)
+  if (d_cnt) {
+    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, nullptr, nullptr, s);
+    h->launches += launch_feacnt(h->tab, h->prm, slot, U, d_cnt, flags, pos, h->cub.p, h->cub.bytes, s);
+    h->launches += launch_pull_view(h->tab, slot, U, u_w, u_vrow, s);
+  } else {
+    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, u_w, u_vrow, s);
+  }
+  FmView v;
+  memset(&v, 0, sizeof(v));
+  v.wbase = u_w; v.w_pos = nullptr;
+  v.vbase = h->tab.V; v.v_pos = u_vrow; v.vstride = ks; v.dense = 0;
+  if (is_train) {
+    DFB_TRY(h->ensure(h->gw, U * sizeof(float)));
+    DFB_CUDA(h, cudaMemsetAsync(h->gw.p, 0, U * sizeof(float), s));
+    if (h->prm.V_dim > 0) {
+      DFB_TRY(h->ensure(h->gV, U * (size_t)ks * sizeof(float)));
+      DFB_CUDA(h, cudaMemsetAsync(h->gV.p, 0, U * (size_t)ks * sizeof(float), s));
+      if (d_val) {
+        DFB_TRY(h->ensure(h->gxxp, U * sizeof(float)));
+        DFB_CUDA(h, cudaMemsetAsync(h->gxxp.p, 0, U * sizeof(float), s));
+      }
+    }
+    v.gwbase = h->gw.as<float>(); v.gw_pos = nullptr;
+    v.gvbase = h->gV.as<float>(); v.gv_pos = nullptr; v.gvstride = ks;
+    v.gxxp = d_val ? h->gxxp.as<float>() : nullptr;
+  }
+  FmBatch b;
+  memset(&b, 0, sizeof(b));
+  b.nrows = nrows; b.offset = d_off; b.index = d_idx; b.value = d_val; b.label = d_lab;
+  b.pred_in = nullptr; b.pred_io = h->pred.as<float>(); b.pred_acc = 0;
+  b.V_dim = h->prm.V_dim; b.train = is_train; b.prog = h->tab.prog;
+  if (nrows) {
+    int nl = launch_fm(b, v, h->force_generic, s);
+    if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
+    h->launches += nl;
+  }
+  if (h->compute_auc && nrows) {
+    DFB_TRY(h->ensure(h->auc_k, nrows * sizeof(float)));
+    DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
+    size_t sb = sort_tmp_bytes(nrows);
+    if (sb > h->cub.bytes) DFB_TRY(h->ensure(h->cub, sb));
+    h->launches += launch_auc(d_lab, h->pred.as<float>(), nrows, nullptr, nullptr, h->auc_k.as<float>(),
+                              h->auc_v.as<float>(), h->cub.p, h->cub.bytes, &h->tab.prog->auc, s);
+  }
+  if (is_train) {
+    // Push(kGradient): FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
+    h->launches += launch_update_dense(h->tab, h->prm, slot, u_vrow, 0, U, h->gw.as<float>(),
+                                       d_val ? h->gxxp.as<float>() : nullptr, h->gV.as<float>(), flags, 1, s);
+    h->launches += launch_initv(h->tab, h->prm, slot, U, flags, pos, h->cub.p, h->cub.bytes, s);
+  } else {
+    h->launches += launch_penalty(h->prm, h->tab.prog, u_w, u_vrow, h->tab.V, ks, 0, U, s);
+  }
+  DFB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int check_csr(dfb_engine* h, size_t nrows, const uint64_t* offset) {
+  if (nrows && !offset) return h->fail(DFB_ERR_INVALID, "offset is NULL");
+  if (nrows && offset[0] != 0) return h->fail(DFB_ERR_INVALID, "offset[0] must be 0 (fm_loss.h:88 assumes it)");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dfb_last_error(dfb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_handle* out) {
+  if (!out) { g_create_error = "out is NULL"; return DFB_ERR_INVALID; }
+  *out = nullptr;
+  dfb_engine* h = new dfb_engine();
+  // defaults and ranges: src/sgd/sgd_param.h:94-106
+  Params& p = h->prm;
+  p.l1 = 1.f; p.l2 = 0.f; p.V_l2 = .01f; p.lr = .01f; p.lr_beta = 1.f; p.V_lr = .01f; p.V_lr_beta = 1.f;
+  p.V_init_scale = .01f; p.V_threshold = 10; p.V_dim = -1; p.seed = 0;
+  long long table_capacity = 1 << 20, v_capacity = -1;
+  struct FR { const char* name; float* dst; float lo, hi; };
+  FR fr[] = {{"l1", &p.l1, 0, 1e10f}, {"l2", &p.l2, 0, 1e10f}, {"V_l2", &p.V_l2, 0, 1e10f},
+             {"lr", &p.lr, 0, 10}, {"lr_beta", &p.lr_beta, 0, 1e10f}, {"V_lr", &p.V_lr, 0, 1e10f},
+             {"V_lr_beta", &p.V_lr_beta, 0, 10}, {"V_init_scale", &p.V_init_scale, 0, 10}};
+  auto bad = [&](const std::string& m) {
+    g_create_error = m;
+    delete h;
+    return (int)DFB_ERR_PARAM;
+  };
+  for (int i = 0; i < n; ++i) {
+    const std::string k = keys[i] ? keys[i] : "", v = vals[i] ? vals[i] : "";
+    bool used = false;
+    for (auto& f : fr) {
+      if (k == f.name) {
+        float x;
+        if (!parse_float(v, &x)) return bad("Invalid Parameter format for " + k + " expect float but value='" + v + "'");
+        if (!(x >= f.lo && x <= f.hi)) return bad("value " + v + " for Parameter " + k + " exceed bound [" + std::to_string(f.lo) + "," + std::to_string(f.hi) + "]");
+        *f.dst = x;
+        used = true;
+      }
+    }
+    if (used) continue;
+    long long x = 0;
+    auto need_int = [&](long long lo, long long hi) {
+      if (!parse_i64(v, &x)) { g_create_error = "Invalid Parameter format for " + k + " expect int but value='" + v + "'"; return false; }
+      if (x < lo || x > hi) { g_create_error = "value " + v + " for Parameter " + k + " out of range"; return false; }
+      return true;
+    };
+    if (k == "V_dim") { if (!need_int(0, 10000)) { delete h; return DFB_ERR_PARAM; } p.V_dim = (int)x; }
+    else if (k == "V_threshold") { if (!need_int(-2147483647LL, 2147483647LL)) { delete h; return DFB_ERR_PARAM; } p.V_threshold = (int)x; }
+    else if (k == "seed") { if (!need_int(0, 4294967295LL)) { delete h; return DFB_ERR_PARAM; } p.seed = (unsigned)x; }
+    else if (k == "device") { if (!need_int(0, 1023)) { delete h; return DFB_ERR_PARAM; } h->device = (int)x; }
+    else if (k == "table_capacity") { if (!need_int(1, 1LL << 30)) { delete h; return DFB_ERR_PARAM; } table_capacity = x; }
+    else if (k == "V_capacity") { if (!need_int(0, 1LL << 30)) { delete h; return DFB_ERR_PARAM; } v_capacity = x; }
+    else if (k == "compute_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->compute_auc = (int)x; }
+    else if (k == "force_generic") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->force_generic = (int)x; }
+    else h->unknown.push_back(std::make_pair(k, v));
+  }
+  if (p.V_dim < 0) return bad("Required parameter V_dim of int is not presented");   // sgd_param.h:104
+  if (v_capacity < 0) v_capacity = table_capacity;
+  if (p.V_dim == 0) v_capacity = 0;
+
+  cudaError_t e;
+  auto cfail = [&](const char* what) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    delete h;
+    return (int)DFB_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(h->device)) != cudaSuccess) return cfail("cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
+  if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
+  for (auto& s : h->in) {
+    if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
+  }
+  Table& t = h->tab;
+  t.max_keys = (uint64_t)table_capacity;
+  t.cap = next_pow2(2 * t.max_keys);
+  if (t.cap < 1024) t.cap = 1024;
+  if (t.cap > (1ULL << 31)) { g_create_error = "table_capacity too large (slots are 31-bit)"; delete h; return DFB_ERR_PARAM; }
+  t.mask = t.cap - 1;
+  t.ks = (p.V_dim + 3) / 4 * 4;
+  t.vcap = (uint64_t)v_capacity;
+  if ((e = cudaMalloc(&t.tab, t.cap * sizeof(Entry))) != cudaSuccess) return cfail("cudaMalloc(table)");
+  if (t.vcap && t.ks) {
+    size_t vb = (size_t)t.vcap * t.ks * sizeof(float);
+    if ((e = cudaMalloc(&t.V, vb)) != cudaSuccess) return cfail("cudaMalloc(V)");
+    if ((e = cudaMalloc(&t.Vcg, vb)) != cudaSuccess) return cfail("cudaMalloc(Vcg)");
+  }
+  if ((e = cudaMalloc(&t.state, sizeof(TableState))) != cudaSuccess) return cfail("cudaMalloc(state)");
+  if ((e = cudaMalloc(&t.prog, 2 * sizeof(DevProgress))) != cudaSuccess) return cfail("cudaMalloc(prog)");
+  if ((e = cudaMemset(t.prog, 0, 2 * sizeof(DevProgress))) != cudaSuccess) return cfail("cudaMemset(prog)");
+  if ((e = cudaHostAlloc(&h->h_prog, sizeof(DevProgress), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
+  if ((e = cudaHostAlloc(&h->h_nvals, sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
+  memset(h->h_prog, 0, sizeof(DevProgress));
+  h->launches += launch_table_init(t, p.seed, h->stream);
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cfail("table init");
+  *out = h;
+  return DFB_OK;
+}
+
+int dfb_destroy(dfb_handle h) {
+  if (!h) return DFB_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
+                    &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
+                    &h->a_val, &h->a_lab, &h->a_w, &h->a_wpos, &h->a_vpos, &h->a_pred, &h->a_grad, &h->scal,
+                    &h->hasv, &h->rV, &h->rcg, &h->nvals};
+  for (auto* b : bufs) if (b->p) cudaFree(b->p);
+  for (auto& s : h->in) {
+    DevBuf* ib[] = {&s.off, &s.idx, &s.val, &s.lab, &s.keys, &s.cnt};
+    for (auto* b : ib) if (b->p) cudaFree(b->p);
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+  }
+  if (h->tab.tab) cudaFree(h->tab.tab);
+  if (h->tab.V) cudaFree(h->tab.V);
+  if (h->tab.Vcg) cudaFree(h->tab.Vcg);
+  if (h->tab.state) cudaFree(h->tab.state);
+  if (h->tab.prog) cudaFree(h->tab.prog);
+  if (h->h_prog) cudaFreeHost(h->h_prog);
+  if (h->h_nvals) cudaFreeHost(h->h_nvals);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return DFB_OK;
+}
+
+int dfb_num_unknown_kwargs(dfb_handle h) { return h ? (int)h->unknown.size() : 0; }
+int dfb_unknown_kwarg(dfb_handle h, int i, const char** key, const char** val) {
+  if (!h || i < 0 || i >= (int)h->unknown.size()) return DFB_ERR_INVALID;
+  *key = h->unknown[i].first.c_str();
+  *val = h->unknown[i].second.c_str();
+  return DFB_OK;
+}
+uint64_t dfb_launch_count(dfb_handle h) { return h ? h->launches : 0; }
+void* dfb_stream(dfb_handle h) { return h ? (void*)h->stream : nullptr; }
+int dfb_row_stride(dfb_handle h) { return h ? h->tab.ks : 0; }
+
+int dfb_table_stats(dfb_handle h, uint64_t* n_keys, uint64_t* n_vrows, uint64_t* capacity, uint64_t* v_capacity) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  TableState st;
+  DFB_CUDA(h, cudaMemcpyAsync(&st, h->tab.state, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (n_keys) *n_keys = st.n_keys;
+  if (n_vrows) *n_vrows = st.n_vrows;
+  if (capacity) *capacity = h->tab.max_keys;
+  if (v_capacity) *v_capacity = h->tab.vcap;
+  return DFB_OK;
+}
+
+int dfb_rng_state(dfb_handle h, uint32_t* seed) {
+  if (!h || !seed) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  TableState st;
+  DFB_CUDA(h, cudaMemcpyAsync(&st, h->tab.state, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  *seed = st.seed;
+  return DFB_OK;
+}
+
+int dfb_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return DFB_ERR_INVALID;
+  return cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? DFB_OK : DFB_ERR_CUDA;
+}
+int dfb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? DFB_OK : DFB_ERR_CUDA; }
+
+// ------------------------------------------------------------------------------------------
+// (A) API-faithful path
+// ------------------------------------------------------------------------------------------
+int dfb_push_feacnt(dfb_handle h, const uint64_t* keys, size_t n, const float* cnt) {
+  if (!h) return DFB_ERR_INVALID;
+  if (n && (!keys || !cnt)) return h->fail(DFB_ERR_INVALID, "keys/cnt is NULL");
+  if (n > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "too many keys");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  DFB_TRY(h2d(h, h->keys, keys, n * sizeof(uint64_t), s));
+  DFB_TRY(h2d(h, h->cnt, cnt, n * sizeof(float), s));
+  DFB_TRY(ensure_key_ws(h, n));
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, h->cnt.as<float>(), h->flags.as<int>(),
+                               h->pos.as<int>(), h->cub.p, h->cub.bytes, s);
+  return sync_and_check(h);
+}
+
+int dfb_pull(dfb_handle h, const uint64_t* keys, size_t n, float* vals_out, size_t vals_cap, int* lens_out,
+             size_t* nvals, size_t* nlens) {
+  if (!h) return DFB_ERR_INVALID;
+  if (!nvals || !nlens) return h->fail(DFB_ERR_INVALID, "nvals/nlens is NULL");
+  if (n && (!keys || !vals_out)) return h->fail(DFB_ERR_INVALID, "keys/vals_out is NULL");
+  if (n > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "too many keys");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int k = h->prm.V_dim;
+  *nvals = 0; *nlens = 0;
+  if (n == 0) return DFB_OK;
+  DFB_TRY(h2d(h, h->keys, keys, n * sizeof(uint64_t), s));
+  DFB_TRY(ensure_key_ws(h, n));
+  if (k == 0) {
+    if (vals_cap < n) return h->fail(DFB_ERR_INVALID, "vals_out too small");
+    h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), h->u_w.as<float>(),
+                                 h->u_vrow.as<int>(), s);
+    DFB_CUDA(h, cudaMemcpyAsync(vals_out, h->u_w.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DFB_TRY(sync_and_check(h));
+    *nvals = n; *nlens = 0;   // lens->resize(V_dim == 0 ? 0 : size), sgd_updater.cc:40
+    return DFB_OK;
+  }
+  if (!lens_out) return h->fail(DFB_ERR_INVALID, "lens_out is NULL");
+  if ((unsigned long long)n * (unsigned long long)(k + 1) > 0x7fffffffULL)
+    return h->fail(DFB_ERR_INVALID, "pull too large for 31-bit positions (the reference's int p overflows too)");
+  DFB_TRY(h->ensure(h->lens, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->vals, n * (size_t)(k + 1) * sizeof(float)));
+  DFB_TRY(h->ensure(h->nvals, sizeof(unsigned long long)));
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_pack_ragged(h->tab, h->prm, h->slot.as<int>(), n, h->lens.as<int>(), h->pos.as<int>(),
+                                    h->vals.as<float>(), h->nvals.as<unsigned long long>(), h->cub.p,
+                                    h->cub.bytes, s);
+  DFB_CUDA(h, cudaMemcpyAsync(h->h_nvals, h->nvals.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaMemcpyAsync(lens_out, h->lens.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  DFB_TRY(sync_and_check(h));
+  const size_t nv = (size_t)*h->h_nvals;
+  if (nv > vals_cap) return h->fail(DFB_ERR_INVALID, "vals_out too small");
+  DFB_CUDA(h, cudaMemcpyAsync(vals_out, h->vals.p, nv * sizeof(float), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaStreamSynchronize(s));
+  *nvals = nv; *nlens = n;
+  return DFB_OK;
+}
+
+int dfb_push_grad(dfb_handle h, const uint64_t* keys, size_t n, const float* grads, size_t nvals,
+                  const int* lens, size_t nlens) {
+  if (!h) return DFB_ERR_INVALID;
+  if (n && (!keys || !grads)) return h->fail(DFB_ERR_INVALID, "keys/grads is NULL");
+  if (n > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "too many keys");
+  const bool w_only = nlens == 0;   // sgd_updater.cc:77-82
+  if (w_only) { if (nvals != n) return h->fail(DFB_ERR_INVALID, "CHECK_EQ(values.size(), size) failed"); }
+  else {
+    if (nlens != n || !lens) return h->fail(DFB_ERR_INVALID, "CHECK_EQ(lens.size(), size) failed");
+    unsigned long long tot = 0;
+    for (size_t i = 0; i < n; ++i) {
+      if (lens[i] < 1) return h->fail(DFB_ERR_INVALID, "lens[i] < 1");
+      tot += (unsigned long long)lens[i];
+    }
+    if (tot != nvals) return h->fail(DFB_ERR_INVALID, "CHECK_EQ(p, values.size()) failed");   // :99
+    if (tot > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "push too large for 31-bit positions");
+  }
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  if (n == 0) return DFB_OK;
+  DFB_TRY(h2d(h, h->keys, keys, n * sizeof(uint64_t), s));
+  DFB_TRY(h2d(h, h->vals, grads, nvals * sizeof(float), s));
+  DFB_TRY(ensure_key_ws(h, n));
+  const int* d_lens = nullptr;
+  if (!w_only) {
+    DFB_TRY(h2d(h, h->lens, lens, n * sizeof(int), s));
+    d_lens = h->lens.as<int>();
+    h->launches += launch_lens_scan(d_lens, n, h->pos.as<int>(), h->cub.p, h->cub.bytes, s);
+  }
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_update_ragged(h->tab, h->prm, h->slot.as<int>(), n, h->vals.as<float>(), d_lens,
+                                      h->pos.as<int>(), h->flags.as<int>(), s);
+  h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, h->flags.as<int>(), h->pos.as<int>(),
+                              h->cub.p, h->cub.bytes, s);
+  return sync_and_check(h);
+}
+
+static int stage_fm_inputs(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index,
+                           const float* value, const float* weights, size_t nweights, const int* w_pos,
+                           const int* V_pos, size_t npos, size_t* nnz_out) {
+  DFB_TRY(check_csr(h, nrows, offset));
+  const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
+  if (nnz && !index) return h->fail(DFB_ERR_INVALID, "index is NULL");
+  if (nweights && !weights) return h->fail(DFB_ERR_INVALID, "weights is NULL");
+  if ((w_pos == nullptr) != (V_pos == nullptr)) return h->fail(DFB_ERR_INVALID, "w_pos and V_pos must both be given or both be NULL");
+  if (h->prm.V_dim > 0 && !V_pos) return h->fail(DFB_ERR_INVALID, "V_pos is required when V_dim > 0");
+  cudaStream_t s = h->stream;
+  DFB_TRY(h2d(h, h->a_off, offset, (nrows + 1) * sizeof(uint64_t), s));
+  DFB_TRY(h2d(h, h->a_idx, index, nnz * sizeof(uint32_t), s));
+  if (value) DFB_TRY(h2d(h, h->a_val, value, nnz * sizeof(float), s));
+  DFB_TRY(h2d(h, h->a_w, weights, nweights * sizeof(float), s));
+  if (w_pos) {
+    DFB_TRY(h2d(h, h->a_wpos, w_pos, npos * sizeof(int), s));
+    DFB_TRY(h2d(h, h->a_vpos, V_pos, npos * sizeof(int), s));
+  }
+  *nnz_out = nnz;
+  return 0;
+}
+
+int dfb_predict(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index, const float* value,
+                const float* weights, size_t nweights, const int* w_pos, const int* V_pos, size_t npos,
+                float* pred) {
+  if (!h) return DFB_ERR_INVALID;
+  if (nrows == 0) return DFB_OK;
+  if (!pred) return h->fail(DFB_ERR_INVALID, "pred is NULL");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  size_t nnz = 0;
+  DFB_TRY(stage_fm_inputs(h, nrows, offset, index, value, weights, nweights, w_pos, V_pos, npos, &nnz));
+  cudaStream_t s = h->stream;
+  DFB_TRY(h2d(h, h->a_pred, pred, nrows * sizeof(float), s));   // pred is accumulated into
+  FmView v;
+  memset(&v, 0, sizeof(v));
+  v.wbase = h->a_w.as<float>(); v.w_pos = w_pos ? h->a_wpos.as<int>() : nullptr;
+  v.vbase = h->a_w.as<float>(); v.v_pos = V_pos ? h->a_vpos.as<int>() : nullptr; v.vstride = 1;
+  FmBatch b;
+  memset(&b, 0, sizeof(b));
+  b.nrows = nrows; b.offset = h->a_off.as<uint64_t>(); b.index = h->a_idx.as<uint32_t>();
+  b.value = value ? h->a_val.as<float>() : nullptr;
+  b.pred_io = h->a_pred.as<float>(); b.pred_acc = 1; b.V_dim = h->prm.V_dim; b.train = 0;
+  int nl = launch_fm(b, v, 1, s);
+  if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
+  h->launches += nl;
+  DFB_CUDA(h, cudaMemcpyAsync(pred, h->a_pred.p, nrows * sizeof(float), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaStreamSynchronize(s));
+  return DFB_OK;
+}
+
+int dfb_calc_grad(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index, const float* value,
+                  const float* label, const float* weights, size_t nweights, const int* w_pos, const int* V_pos,
+                  size_t npos, const float* pred, float* grad) {
+  if (!h) return DFB_ERR_INVALID;
+  if (nrows == 0) return DFB_OK;
+  if (!pred || !grad || !label) return h->fail(DFB_ERR_INVALID, "pred/grad/label is NULL");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  size_t nnz = 0;
+  DFB_TRY(stage_fm_inputs(h, nrows, offset, index, value, weights, nweights, w_pos, V_pos, npos, &nnz));
+  cudaStream_t s = h->stream;
+  const int k = h->prm.V_dim;
+  DFB_TRY(h2d(h, h->a_pred, pred, nrows * sizeof(float), s));
+  DFB_TRY(h2d(h, h->a_lab, label, nrows * sizeof(float), s));
+  DFB_TRY(h2d(h, h->a_grad, grad, nweights * sizeof(float), s));   // grad is accumulated into
+  if (k > 0) {
+    DFB_TRY(h->ensure(h->gxxp, npos * sizeof(float)));
+    DFB_CUDA(h, cudaMemsetAsync(h->gxxp.p, 0, npos * sizeof(float), s));
+  }
+  FmView v;
+  memset(&v, 0, sizeof(v));
+  v.wbase = h->a_w.as<float>(); v.w_pos = w_pos ? h->a_wpos.as<int>() : nullptr;
+  v.vbase = h->a_w.as<float>(); v.v_pos = V_pos ? h->a_vpos.as<int>() : nullptr; v.vstride = 1;
+  v.gwbase = h->a_grad.as<float>(); v.gw_pos = v.w_pos;
+  v.gvbase = h->a_grad.as<float>(); v.gv_pos = v.v_pos; v.gvstride = 1;
+  v.gxxp = k > 0 ? h->gxxp.as<float>() : nullptr;
+  FmBatch b;
+  memset(&b, 0, sizeof(b));
+  b.nrows = nrows; b.offset = h->a_off.as<uint64_t>(); b.index = h->a_idx.as<uint32_t>();
+  b.value = value ? h->a_val.as<float>() : nullptr; b.label = h->a_lab.as<float>();
+  b.pred_in = h->a_pred.as<float>(); b.pred_io = nullptr; b.pred_acc = 0; b.V_dim = k; b.train = 1;
+  b.prog = nullptr;
+  int nl = launch_fm(b, v, 1, s);
+  if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
+  h->launches += nl;
+  if (k > 0)
+    h->launches += launch_grad_finalize(k, npos, h->a_w.as<float>(), h->a_vpos.as<int>(), h->gxxp.as<float>(),
+                                        h->a_grad.as<float>(), s);
+  DFB_CUDA(h, cudaMemcpyAsync(grad, h->a_grad.p, nweights * sizeof(float), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaStreamSynchronize(s));
+  return DFB_OK;
+}
+
+int dfb_evaluate(dfb_handle h, const float* label, const float* pred, size_t n, float* objv) {
+  if (!h || !objv) return DFB_ERR_INVALID;
+  *objv = 0.f;
+  if (n == 0) return DFB_OK;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  DFB_TRY(h2d(h, h->a_lab, label, n * sizeof(float), s));
+  DFB_TRY(h2d(h, h->a_pred, pred, n * sizeof(float), s));
+  DFB_CUDA(h, cudaMemsetAsync(h->tab.prog + 1, 0, sizeof(DevProgress), s));
+  h->launches += launch_evaluate(h->a_lab.as<float>(), h->a_pred.as<float>(), n, &(h->tab.prog + 1)->loss, s);
+  DevProgress pr;
+  DFB_TRY(fetch_scratch(h, &pr));
+  *objv = (float)pr.loss;
+  return DFB_OK;
+}
+
+int dfb_auc(dfb_handle h, const float* label, const float* pred, size_t n, float* auc_times_n) {
+  if (!h || !auc_times_n) return DFB_ERR_INVALID;
+  *auc_times_n = 0.f;
+  if (n == 0) return DFB_OK;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  DFB_TRY(h2d(h, h->a_lab, label, n * sizeof(float), s));
+  DFB_TRY(h2d(h, h->a_pred, pred, n * sizeof(float), s));
+  DFB_TRY(h->ensure(h->auc_k, n * sizeof(float)));
+  DFB_TRY(h->ensure(h->auc_v, n * sizeof(float)));
+  DFB_TRY(h->ensure(h->cub, sort_tmp_bytes(n)));
+  DFB_CUDA(h, cudaMemsetAsync(h->tab.prog + 1, 0, sizeof(DevProgress), s));
+  h->launches += launch_auc(h->a_lab.as<float>(), h->a_pred.as<float>(), n, nullptr, nullptr, h->auc_k.as<float>(),
+                            h->auc_v.as<float>(), h->cub.p, h->cub.bytes, &(h->tab.prog + 1)->auc, s);
+  DevProgress pr;
+  DFB_TRY(fetch_scratch(h, &pr));
+  *auc_times_n = (float)pr.auc;
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// (B) fused step
+// ------------------------------------------------------------------------------------------
+int dfb_train_step_dev(dfb_handle h, size_t nrows, const uint64_t* d_offset, const uint32_t* d_index,
+                       const float* d_value_or_null, const float* d_label, const uint64_t* d_keys, size_t nkeys,
+                       const float* d_cnt_or_null, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  return step_dev(h, nrows, d_offset, d_index, d_value_or_null, d_label, d_keys, nkeys, d_cnt_or_null, is_train);
+}
+
+int dfb_sync(dfb_handle h) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DFB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return DFB_OK;
+}
+
+int dfb_read_progress(dfb_handle h, dfb_progress* out) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DFB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  return fetch_progress(h, out);
+}
+
+int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index,
+                         const float* value, const float* label, const uint64_t* keys, size_t nkeys,
+                         const float* cnt, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_TRY(check_csr(h, nrows, offset));
+  if (nrows && !label) return h->fail(DFB_ERR_INVALID, "label is NULL");
+  if (nkeys && !keys) return h->fail(DFB_ERR_INVALID, "keys is NULL");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
+  if (nnz && !index) return h->fail(DFB_ERR_INVALID, "index is NULL");
+  auto& in = h->in[h->seq & 1];
+  cudaStream_t cs = h->copy_stream;
+  // the copy of batch t+1 may overwrite set b only after batch t-1 (same set) was consumed
+  if (h->seq >= 2) DFB_CUDA(h, cudaStreamWaitEvent(cs, in.consumed, 0));
+  DFB_TRY(h2d(h, in.off, offset, (nrows + 1) * sizeof(uint64_t), cs));
+  DFB_TRY(h2d(h, in.idx, index, nnz * sizeof(uint32_t), cs));
+  if (value) DFB_TRY(h2d(h, in.val, value, nnz * sizeof(float), cs));
+  DFB_TRY(h2d(h, in.lab, label, nrows * sizeof(float), cs));
+  DFB_TRY(h2d(h, in.keys, keys, nkeys * sizeof(uint64_t), cs));
+  if (cnt) DFB_TRY(h2d(h, in.cnt, cnt, nkeys * sizeof(float), cs));
+  DFB_CUDA(h, cudaEventRecord(in.copied, cs));
+  DFB_CUDA(h, cudaStreamWaitEvent(h->stream, in.copied, 0));
+  int rc = step_dev(h, nrows, in.off.as<uint64_t>(), in.idx.as<uint32_t>(), value ? in.val.as<float>() : nullptr,
+                    in.lab.as<float>(), in.keys.as<uint64_t>(), nkeys, cnt ? in.cnt.as<float>() : nullptr,
+                    is_train);
+  DFB_CUDA(h, cudaEventRecord(in.consumed, h->stream));
+  h->seq++;
+  return rc;
+}
+
+int dfb_train_step(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index, const float* value,
+                   const float* label, const uint64_t* keys, size_t nkeys, const float* cnt, int is_train,
+                   dfb_progress* out, float* pred_out) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_TRY(dfb_train_step_async(h, nrows, offset, index, value, label, keys, nkeys, cnt, is_train));
+  if (pred_out && nrows)
+    DFB_CUDA(h, cudaMemcpyAsync(pred_out, h->pred.p, nrows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  return fetch_progress(h, out);
+}
+
+int dfb_read_entries(dfb_handle h, const uint64_t* keys, size_t n, float* scal_out, int* has_V_out, float* V_out,
+                     float* cg_out) {
+  if (!h) return DFB_ERR_INVALID;
+  if (n == 0) return DFB_OK;
+  if (!keys || !scal_out || !has_V_out) return h->fail(DFB_ERR_INVALID, "NULL argument");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int k = h->prm.V_dim;
+  DFB_TRY(h2d(h, h->keys, keys, n * sizeof(uint64_t), s));
+  DFB_TRY(ensure_key_ws(h, n));
+  DFB_TRY(h->ensure(h->scal, n * 4 * sizeof(float)));
+  DFB_TRY(h->ensure(h->hasv, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->rV, n * (size_t)(k ? k : 1) * sizeof(float)));
+  DFB_TRY(h->ensure(h->rcg, n * (size_t)(k ? k : 1) * sizeof(float)));
+  DFB_CUDA(h, cudaMemsetAsync(h->rV.p, 0, n * (size_t)(k ? k : 1) * sizeof(float), s));
+  DFB_CUDA(h, cudaMemsetAsync(h->rcg.p, 0, n * (size_t)(k ? k : 1) * sizeof(float), s));
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, false, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_read_entries(h->tab, h->slot.as<int>(), n, h->scal.as<float>(), h->hasv.as<int>(),
+                                     h->rV.as<float>(), h->rcg.as<float>(), k, s);
+  DFB_CUDA(h, cudaMemcpyAsync(scal_out, h->scal.p, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaMemcpyAsync(has_V_out, h->hasv.p, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (V_out && k) DFB_CUDA(h, cudaMemcpyAsync(V_out, h->rV.p, n * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (cg_out && k) DFB_CUDA(h, cudaMemcpyAsync(cg_out, h->rcg.p, n * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaStreamSynchronize(s));
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sharding
+// ------------------------------------------------------------------------------------------
+uint32_t dfb_key_owner(uint64_t key, uint32_t S) {
+  if (S == 0) return 0;
+  const uint64_t width = UINT64_MAX / (uint64_t)S;   // postoffice.cc:130-134
+  const uint64_t o = key / width;
+  return (uint32_t)(o >= S ? S - 1 : o);
+}
+
+int dfb_shard_bounds(const uint64_t* keys, size_t n, uint32_t S, size_t* bounds) {
+  if (!bounds || S == 0 || (n && !keys)) return DFB_ERR_INVALID;
+  const uint64_t width = UINT64_MAX / (uint64_t)S;
+  bounds[0] = 0;
+  for (uint32_t i = 1; i < S; ++i) {
+    // first key >= width*i  (lower_bound, like DefaultSlicer kv_app.h:416-429)
+    const uint64_t lo_key = width * i;
+    size_t lo = bounds[i - 1], hi = n;
+    while (lo < hi) {
+      size_t mid = lo + (hi - lo) / 2;
+      if (keys[mid] < lo_key) lo = mid + 1; else hi = mid;
+    }
+    bounds[i] = lo;
+  }
+  bounds[S] = n;
+  return DFB_OK;
+}
+
+int dfb_dev_feacnt(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_cnt) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  if (n == 0) return DFB_OK;
+  DFB_TRY(ensure_key_ws(h, n));
+  cudaStream_t s = h->stream;
+  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, d_cnt, h->flags.as<int>(), h->pos.as<int>(),
+                               h->cub.p, h->cub.bytes, s);
+  DFB_CUDA(h, cudaGetLastError());
+  return DFB_OK;
+}
+
+int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w_out, int* d_hasv_out,
+                      float* d_V_out) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  if (n == 0) return DFB_OK;
+  DFB_TRY(ensure_key_ws(h, n));
+  cudaStream_t s = h->stream;
+  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_gather_rows(h->tab, h->slot.as<int>(), n, d_w_out, d_hasv_out,
+                                    h->prm.V_dim > 0 ? d_V_out : nullptr, s);
+  DFB_CUDA(h, cudaGetLastError());
+  return DFB_OK;
+}
+
+int dfb_dev_fm_step(dfb_handle h, size_t nrows, const uint64_t* d_offset, const uint32_t* d_index,
+                    const float* d_value, const float* d_label, size_t nkeys, const float* d_w, const int* d_hasv,
+                    const float* d_V, int is_train, float* d_gw_out, float* d_gxxp_out, float* d_gV_out) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const int ks = h->tab.ks, k = h->prm.V_dim;
+  DFB_TRY(h->ensure(h->pred, nrows * sizeof(float)));
+  FmView v;
+  memset(&v, 0, sizeof(v));
+  v.wbase = d_w; v.w_pos = nullptr;
+  v.vbase = d_V; v.v_pos = d_hasv; v.vstride = ks; v.dense = 1;
+  if (is_train) {
+    if (!d_gw_out || (k > 0 && !d_gV_out) || (k > 0 && d_value && !d_gxxp_out))
+      return h->fail(DFB_ERR_INVALID, "gradient outputs are NULL");
+    DFB_CUDA(h, cudaMemsetAsync(d_gw_out, 0, nkeys * sizeof(float), s));
+    if (k > 0) DFB_CUDA(h, cudaMemsetAsync(d_gV_out, 0, nkeys * (size_t)ks * sizeof(float), s));
+    if (k > 0 && d_gxxp_out) DFB_CUDA(h, cudaMemsetAsync(d_gxxp_out, 0, nkeys * sizeof(float), s));
+    v.gwbase = d_gw_out; v.gvbase = d_gV_out; v.gvstride = ks;
+    v.gxxp = (k > 0 && d_value) ? d_gxxp_out : nullptr;
+  }
+  FmBatch b;
+  memset(&b, 0, sizeof(b));
+  b.nrows = nrows; b.offset = d_offset; b.index = d_index; b.value = d_value; b.label = d_label;
+  b.pred_io = h->pred.as<float>(); b.V_dim = k; b.train = is_train; b.prog = h->tab.prog;
+  if (nrows) {
+    int nl = launch_fm(b, v, h->force_generic, s);
+    if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
+    h->launches += nl;
+  }
+  if (h->compute_auc && nrows) {
+    DFB_TRY(h->ensure(h->auc_k, nrows * sizeof(float)));
+    DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
+    DFB_TRY(h->ensure(h->cub, sort_tmp_bytes(nrows)));
+    h->launches += launch_auc(d_label, h->pred.as<float>(), nrows, nullptr, nullptr, h->auc_k.as<float>(),
+                              h->auc_v.as<float>(), h->cub.p, h->cub.bytes, &h->tab.prog->auc, s);
+  }
+  // the worker evaluates the penalty of what it pulled (sgd_learner.cc:148)
+  h->launches += launch_penalty(h->prm, h->tab.prog, d_w, d_hasv, d_V, ks, 1, nkeys, s);
+  DFB_CUDA(h, cudaGetLastError());
+  return DFB_OK;
+}
+
+int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_gw, const float* d_gxxp,
+                      const int* d_hasv, const float* d_gV) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  if (n == 0) return DFB_OK;
+  DFB_TRY(ensure_key_ws(h, n));
+  cudaStream_t s = h->stream;
+  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_update_dense(h->tab, h->prm, h->slot.as<int>(), d_hasv, 1, n, d_gw, d_gxxp, d_gV,
+                                     h->flags.as<int>(), 0, s);
+  h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, h->flags.as<int>(), h->pos.as<int>(),
+                              h->cub.p, h->cub.bytes, s);
+  DFB_CUDA(h, cudaGetLastError());
+  return DFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// difacto_b200/csrc/kernels_fm.cu -- FM forward (+ fused backward scatter) for sm_100a.
+//
+// Restates, for the GPU, FMLoss::Predict (src/loss/fm_loss.h:67-119: SpMV::Times,
+// 2x SpMM::Times, row reduce, clamp), Loss::Evaluate (include/difacto/loss.h:57-66) and
+// FMLoss::CalcGrad (fm_loss.h:148-199: p = -y/(1+exp(y pred)), SpMV::TransTimes,
+// SpMM::TransTimes) of the reference as ONE pass per CSR row:
+//
+//   phase 1  gather the k-wide V rows of the row's active features (coalesced 16-byte lanes,
+//            UNR independent loads in flight per lane), accumulate XV = sum x V and
+//            sum (x V)^2 in registers, warp-shuffle reduce over k -> pred, logloss
+//   phase 2  (training) p from the clamped pred, then scatter x p XV into the per-key gradient
+//            rows with vector fp32 reductions (red.global.add.v4.f32), x p into grad_w and
+//            x^2 p into XXp.  The "- V_j XXp_j" term (fm_loss.h:181-188) needs V once per
+//            unique key, not per nnz, so it is applied where V is read anyway: in the fused
+//            FTRL/AdaGrad kernel (kernels_table.cu) or in grad_finalize below.
+//
+// The whole path is HBM-bound (about 0.5 FLOP/B): no tensor cores on purpose.
+#include "dfb_internal.cuh"
+
+#include <math.h>
+
+namespace dfb {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float4 ldg128(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ void red_add(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// logloss of one row: log(1 + exp(-y pred)), y = label > 0 ? 1 : -1 (loss.h:62-63)
+__device__ __forceinline__ float row_logloss(float label, float pred) {
+  float y = label > 0.f ? 1.f : -1.f;
+  return logf(1.f + expf(-y * pred));
+}
+
+// p = -y / (1 + exp(y pred))  (fm_loss.h:157-161)
+__device__ __forceinline__ float row_p(float label, float pred) {
+  float y = label > 0.f ? 1.f : -1.f;
+  return -y / (1.f + expf(y * pred));
+}
+
+__device__ __forceinline__ void block_add_loss(float loss_acc, size_t nrows, DevProgress* prog) {
+  __shared__ float red_s[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // lane 0 of each warp holds that warp's partial
+  if (lane == 0) red_s[wid] = loss_acc;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    float v = lane < nw ? red_s[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0 && prog) {
+      atomicAdd(&prog->loss, (double)v);
+      if (blockIdx.x == 0) atomicAdd(&prog->nrows, (unsigned long long)nrows);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// fast path: K in {8,16,32,64,128}, 16-byte aligned rows
+// ---------------------------------------------------------------------------------------
+template <int K, bool TRAIN, bool HAS_VAL>
+__global__ void __launch_bounds__(256) k_fm_fast(FmBatch b, FmView v) {
+  constexpr int LPR = K / 4;                 // lanes per V row, one float4 each
+  constexpr int G = 32 / LPR;                // V rows fetched by one warp-wide load
+  constexpr int UNR = (32 / G) < 8 ? (32 / G) : 8;   // independent loads in flight per lane
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  float loss_acc = 0.f;
+
+  for (size_t row = warp0; row < b.nrows; row += nwarps) {
+    const uint64_t o0 = b.offset[row], o1 = b.offset[row + 1];
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc2 = 0.f, wsum = 0.f;
+
+    for (uint64_t c = o0; c < o1; c += 32) {
+      const uint64_t j = c + lane;
+      const bool valid = j < o1;
+      uint32_t u = 0;
+      float x = 0.f, w = 0.f;
+      int vr = -1;
+      if (valid) {
+        u = __ldg(b.index + j);
+        x = HAS_VAL ? __ldg(b.value + j) : 1.f;
+        const int wp = v.w_pos ? __ldg(v.w_pos + u) : (int)u;
+        w = wp >= 0 ? __ldg(v.wbase + wp) : 0.f;
+        vr = __ldg(v.v_pos + u);
+        if (v.dense && vr >= 0) vr = (int)u;
+      }
+      wsum = fmaf(x, w, wsum);
+      const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
+      for (int t0 = 0; t0 < cnt; t0 += G * UNR) {
+        float4 vv[UNR];
+        float xs[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const int t = t0 + q * G + grp;
+          const int vr_t = __shfl_sync(kFull, vr, t & 31);
+          const float x_t = __shfl_sync(kFull, x, t & 31);
+          const bool ok = (t < cnt) && (vr_t >= 0);
+          xs[q] = ok ? x_t : 0.f;
+          vv[q] = ok ? ldg128(v.vbase + (long long)vr_t * v.vstride + sub * 4)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const float a0 = xs[q] * vv[q].x, a1 = xs[q] * vv[q].y;
+          const float a2 = xs[q] * vv[q].z, a3 = xs[q] * vv[q].w;
+          xv.x += a0; xv.y += a1; xv.z += a2; xv.w += a3;
+          acc2 = fmaf(a0, a0, acc2); acc2 = fmaf(a1, a1, acc2);
+          acc2 = fmaf(a2, a2, acc2); acc2 = fmaf(a3, a3, acc2);
+        }
+      }
+    }
+    // combine the G row-groups: afterwards every group holds the full XV for its 4 dims
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      xv.x += __shfl_xor_sync(kFull, xv.x, o);
+      xv.y += __shfl_xor_sync(kFull, xv.y, o);
+      xv.z += __shfl_xor_sync(kFull, xv.z, o);
+      xv.w += __shfl_xor_sync(kFull, xv.w, o);
+    }
+    float s1 = grp == 0 ? (xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w) : 0.f;
+    s1 = warp_sum(s1);
+    acc2 = warp_sum(acc2);
+    wsum = warp_sum(wsum);
+    float pred = (b.pred_acc ? b.pred_io[row] : 0.f) + wsum;
+    pred += 0.5f * (s1 - acc2);
+    pred = pred > 20.f ? 20.f : (pred < -20.f ? -20.f : pred);   // fm_loss.h:118
+    const float label = b.label ? __ldg(b.label + row) : 0.f;
+    if (lane == 0) {
+      if (b.pred_io) b.pred_io[row] = pred;
+      if (b.label) loss_acc += row_logloss(label, pred);
+    }
+
+    if (TRAIN) {
+      const float p = row_p(label, b.pred_in ? __ldg(b.pred_in + row) : pred);
+      const float4 gx = make_float4(p * xv.x, p * xv.y, p * xv.z, p * xv.w);
+      for (uint64_t c = o0; c < o1; c += 32) {
+        const uint64_t j = c + lane;
+        const bool valid = j < o1;
+        uint32_t u = 0;
+        float x = 0.f;
+        int vr = -1;
+        if (valid) {
+          u = __ldg(b.index + j);
+          x = HAS_VAL ? __ldg(b.value + j) : 1.f;
+          vr = __ldg(v.v_pos + u);
+          const int gp = v.gw_pos ? __ldg(v.gw_pos + u) : (int)u;
+          if (gp >= 0) red_add(v.gwbase + gp, x * p);
+          if (HAS_VAL && vr >= 0) red_add(v.gxxp + u, x * x * p);
+        }
+        const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
+        for (int t0 = 0; t0 < cnt; t0 += G) {
+          const int t = t0 + grp;
+          const int vr_t = __shfl_sync(kFull, vr, t & 31);
+          const float x_t = __shfl_sync(kFull, x, t & 31);
+          const uint32_t u_t = __shfl_sync(kFull, u, t & 31);
+          if (t < cnt && vr_t >= 0) {
+            const long long r = v.gv_pos ? (long long)__ldg(v.gv_pos + u_t) : (long long)u_t;
+            red_add_v4(v.gvbase + r * v.gvstride + sub * 4, x_t * gx.x, x_t * gx.y, x_t * gx.z,
+                       x_t * gx.w);
+          }
+        }
+      }
+    }
+  }
+  block_add_loss(loss_acc, b.nrows, b.prog);
+}
+
+// ---------------------------------------------------------------------------------------
+// generic path: any V_dim (including 0), unaligned / ragged rows (the pulled layout of the
+// reference: [w_0,(V_0..)][w_1,(V_1..)] with w_pos/V_pos, sgd_updater.cc:46-53)
+// ---------------------------------------------------------------------------------------
+template <bool TRAIN>
+__global__ void __launch_bounds__(128) k_fm_generic(FmBatch b, FmView v) {
+  extern __shared__ float smem[];
+  const int k = b.V_dim;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* xv = smem + (size_t)wid * k;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const bool has_val = b.value != nullptr;
+  float loss_acc = 0.f;
+
+  for (size_t row = warp0; row < b.nrows; row += nwarps) {
+    const uint64_t o0 = b.offset[row], o1 = b.offset[row + 1];
+    for (int l = lane; l < k; l += 32) xv[l] = 0.f;
+    float acc2 = 0.f, wsum = 0.f;
+    for (uint64_t c = o0; c < o1; c += 32) {
+      const uint64_t j = c + lane;
+      const bool valid = j < o1;
+      uint32_t u = 0;
+      float x = 0.f, w = 0.f;
+      long long vr = -1;
+      if (valid) {
+        u = b.index[j];
+        x = has_val ? b.value[j] : 1.f;
+        const int wp = v.w_pos ? v.w_pos[u] : (int)u;
+        w = wp >= 0 ? v.wbase[wp] : 0.f;
+        if (k > 0 && v.v_pos) {
+          vr = v.v_pos[u];
+          if (v.dense && vr >= 0) vr = u;
+        }
+      }
+      wsum = fmaf(x, w, wsum);
+      if (k > 0) {
+        const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
+        for (int t = 0; t < cnt; ++t) {
+          const long long vr_t = __shfl_sync(kFull, vr, t);
+          const float x_t = __shfl_sync(kFull, x, t);
+          if (vr_t < 0) continue;   // warp-uniform
+          const float* rowp = v.vbase + vr_t * v.vstride;
+          for (int l = lane; l < k; l += 32) {
+            const float a = x_t * rowp[l];
+            xv[l] += a;
+            acc2 = fmaf(a, a, acc2);
+          }
+        }
+      }
+    }
+    float pred = (b.pred_acc ? b.pred_io[row] : 0.f);
+    wsum = warp_sum(wsum);
+    pred += wsum;
+    if (k > 0) {   // V_dim == 0 returns before the clamp (fm_loss.h:77)
+      float s1 = 0.f;
+      for (int l = lane; l < k; l += 32) s1 = fmaf(xv[l], xv[l], s1);
+      s1 = warp_sum(s1);
+      acc2 = warp_sum(acc2);
+      pred += 0.5f * (s1 - acc2);
+      pred = pred > 20.f ? 20.f : (pred < -20.f ? -20.f : pred);
+    }
+    const float label = b.label ? b.label[row] : 0.f;
+    if (lane == 0) {
+      if (b.pred_io) b.pred_io[row] = pred;
+      if (b.label) loss_acc += row_logloss(label, pred);
+    }
+    if (TRAIN) {
+      const float p = row_p(label, b.pred_in ? b.pred_in[row] : pred);
+      for (uint64_t c = o0; c < o1; c += 32) {
+        const uint64_t j = c + lane;
+        const bool valid = j < o1;
+        uint32_t u = 0;
+        float x = 0.f;
+        long long gr = -1;
+        if (valid) {
+          u = b.index[j];
+          x = has_val ? b.value[j] : 1.f;
+          const int gp = v.gw_pos ? v.gw_pos[u] : (int)u;
+          if (gp >= 0) red_add(v.gwbase + gp, x * p);
+          if (k > 0 && v.v_pos && v.v_pos[u] >= 0) {
+            gr = v.gv_pos ? (long long)v.gv_pos[u] : (long long)u;
+            if (v.gxxp) red_add(v.gxxp + u, (has_val ? x * x : 1.f) * p);
+          }
+        }
+        if (k > 0) {
+          const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
+          for (int t = 0; t < cnt; ++t) {
+            const long long gr_t = __shfl_sync(kFull, gr, t);
+            const float x_t = __shfl_sync(kFull, x, t);
+            if (gr_t < 0) continue;
+            float* g = v.gvbase + gr_t * v.gvstride;
+            const float xp = x_t * p;
+            for (int l = lane; l < k; l += 32) red_add(g + l, xp * xv[l]);
+          }
+        }
+      }
+    }
+  }
+  block_add_loss(loss_acc, b.nrows, b.prog);
+}
+
+// grad_V -= diag(XXp) V for the ragged layout (fm_loss.h:181-188)
+__global__ void k_grad_finalize(int k, size_t nkeys, const float* weights, const int* V_pos,
+                                const float* xxp, float* grad) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t u = warp0; u < nkeys; u += nwarps) {
+    const int p = V_pos[u];
+    if (p < 0) continue;
+    const float s = xxp[u];
+    for (int l = lane; l < k; l += 32) grad[p + l] -= weights[p + l] * s;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int K>
+int launch_fast_k(const FmBatch& b, const FmView& v, cudaStream_t s) {
+  const int threads = 256;
+  size_t need = (b.nrows + 7) / 8;
+  int grid = (int)(need < (size_t)(148 * 8) ? (need ? need : 1) : (size_t)(148 * 8));
+  const bool hv = b.value != nullptr;
+  if (b.train) {
+    if (hv) k_fm_fast<K, true, true><<<grid, threads, 0, s>>>(b, v);
+    else    k_fm_fast<K, true, false><<<grid, threads, 0, s>>>(b, v);
+  } else {
+    if (hv) k_fm_fast<K, false, true><<<grid, threads, 0, s>>>(b, v);
+    else    k_fm_fast<K, false, false><<<grid, threads, 0, s>>>(b, v);
+  }
+  return 1;
+}
+
+}  // namespace
+
+int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t s) {
+  const int k = b.V_dim;
+  bool fast = !force_generic && (k == 8 || k == 16 || k == 32 || k == 64 || k == 128) &&
+              v.v_pos != nullptr && aligned16(v.vbase) && (v.vstride % 4 == 0);
+  if (fast && b.train) {
+    fast = aligned16(v.gvbase) && (v.gvstride % 4 == 0) && (b.value == nullptr || v.gxxp != nullptr);
+  }
+  if (fast) {
+    switch (k) {
+      case 8: return launch_fast_k<8>(b, v, s);
+      case 16: return launch_fast_k<16>(b, v, s);
+      case 32: return launch_fast_k<32>(b, v, s);
+      case 64: return launch_fast_k<64>(b, v, s);
+      case 128: return launch_fast_k<128>(b, v, s);
+    }
+  }
+  if (k > 0 && v.v_pos == nullptr) return -1;   // V_pos is required when V_dim > 0
+  const int threads = 128;
+  const size_t smem = (size_t)4 * k * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  size_t need = (b.nrows + 3) / 4;
+  int grid = (int)(need < (size_t)(148 * 16) ? (need ? need : 1) : (size_t)(148 * 16));
+  if (b.train) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_fm_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fm_generic<true><<<grid, threads, smem, s>>>(b, v);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_fm_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fm_generic<false><<<grid, threads, smem, s>>>(b, v);
+  }
+  return 1;
+}
+
+int launch_grad_finalize(int V_dim, size_t nkeys, const float* weights, const int* V_pos,
+                         const float* xxp, float* grad, cudaStream_t s) {
+  if (V_dim == 0 || nkeys == 0) return 0;
+  size_t need = (nkeys + 7) / 8;
+  int grid = (int)(need < (size_t)(148 * 8) ? need : (size_t)(148 * 8));
+  k_grad_finalize<<<grid, 256, 0, s>>>(V_dim, nkeys, weights, V_pos, xxp, grad);
+  return 1;
+}
+
+}  // namespace dfb

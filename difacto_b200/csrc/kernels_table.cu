@@ -1,0 +1,660 @@
+// difacto_b200/csrc/kernels_table.cu -- the HBM-resident model table and its per-key kernels.
+//
+// GPU restatement of SGDUpdater (src/sgd/sgd_updater.{h,cc} of the reference):
+//   model_[key]            -> open-addressing hash of 32-byte entries (k_lookup)
+//   Get        cc:32-56    -> k_lookup(+pull) / k_pack_ragged / k_gather_rows
+//   Update(kFeaCount) :62-73 -> k_feacnt (+ InitV pass)
+//   Update(kGradient) :74-98 -> k_update_dense / k_update_ragged
+//   UpdateW (FTRL)   :104-127, UpdateV (AdaGrad) :129-138 -> ftrl_step / adagrad_step, written
+//                       with explicit round-to-nearest intrinsics (no FMA contraction) so that,
+//                       given identical gradients, the state is bit-identical to the reference
+//   InitV            :140-147 -> k_initv: glibc rand_r restated with LCG jump-ahead so that new
+//                       rows consume the random stream in ascending key order like the reference
+// plus Loss::Evaluate (loss.h:57-66), BinClassMetric::AUC (bin_class_metric.h:35-56) and
+// SGDLearner::EvaluatePenalty (sgd_learner.cc:249-273).
+#include "dfb_internal.cuh"
+
+#include <cub/cub.cuh>
+
+#include "../../include/difacto_b200.h"
+
+namespace dfb {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint64_t hash64(uint64_t h) {
+  h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
+  h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
+  h ^= h >> 33;
+  return h;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void raise(DevProgress* prog, int code) { atomicCAS(&prog->err, 0, code); }
+
+__global__ void k_table_init(Entry* tab, uint64_t cap, TableState* st, DevProgress* prog, unsigned seed) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < cap; i += stride) {
+    Entry e;
+    e.key = kEmptyKey; e.vrow = -1; e.pad = 0;
+    e.fea_cnt = 0.f; e.w = 0.f; e.sqrt_g = 0.f; e.z = 0.f;
+    tab[i] = e;
+  }
+  if (i0 == 0) {
+    st->n_keys = 0; st->n_vrows = 0; st->seed = seed; st->pad = 0;
+    prog->loss = 0; prog->penalty = 0; prog->auc = 0;
+    prog->nrows = 0; prog->new_keys = 0; prog->new_vrows = 0; prog->err = 0; prog->pad = 0;
+  }
+}
+
+// model_[key] (sgd_updater.cc:43-45,65-67,86-88): find or default-construct
+template <bool INSERT>
+__global__ void k_lookup(Table t, const uint64_t* __restrict__ keys, size_t n, int* __restrict__ slot_out,
+                         float* __restrict__ w_out, int* __restrict__ vrow_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  int slot = -1;
+  if (key == kEmptyKey) {
+    raise(t.prog, DFB_ERR_INVALID);
+  } else {
+    uint64_t h = hash64(key) & t.mask;
+    for (uint64_t probe = 0; probe <= t.mask; ++probe) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.tab[h].key);
+      if (cur == key) { slot = (int)h; break; }
+      if (cur == kEmptyKey) {
+        if (!INSERT) break;
+        const unsigned long long prev = atomicCAS(&t.tab[h].key, kEmptyKey, key);
+        if (prev == kEmptyKey) {
+          const unsigned long long nk = atomicAdd(&t.state->n_keys, 1ULL) + 1;
+          atomicAdd(&t.prog->new_keys, 1ULL);
+          if (nk > t.max_keys) raise(t.prog, DFB_ERR_CAPACITY);
+          slot = (int)h;
+          break;
+        }
+        if (prev == key) { slot = (int)h; break; }
+      }
+      h = (h + 1) & t.mask;
+    }
+    if (INSERT && slot < 0) raise(t.prog, DFB_ERR_CAPACITY);
+  }
+  slot_out[i] = slot;
+  if (w_out) {
+    float w = 0.f;
+    int vr = -1;
+    if (slot >= 0) {
+      // second half of the entry {fea_cnt, w, sqrt_g, z}; first half holds vrow
+      w = t.tab[slot].w;
+      vr = t.tab[slot].vrow;
+    }
+    w_out[i] = w;
+    vrow_out[i] = vr;
+  }
+}
+
+// SGDUpdater::Update(kFeaCount), sgd_updater.cc:62-73
+__global__ void k_feacnt(Table t, Params p, const int* __restrict__ slot, size_t n,
+                         const float* __restrict__ cnt, int* __restrict__ flags) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = slot[i];
+  int f = 0;
+  if (s >= 0) {
+    Entry* e = &t.tab[s];
+    const float fc = __fadd_rn(e->fea_cnt, cnt[i]);
+    e->fea_cnt = fc;
+    if (p.V_dim > 0 && e->vrow < 0 && e->w != 0.f && fc > (float)p.V_threshold) f = 1;
+  }
+  flags[i] = f;
+}
+
+// ---- glibc rand_r restated: next = next*1103515245 + 12345 three times per draw ----
+struct Affine { unsigned a, c; };   // x -> a*x + c  (mod 2^32)
+__device__ __forceinline__ Affine compose(Affine f, Affine g) {   // g after f
+  Affine r; r.a = g.a * f.a; r.c = g.a * f.c + g.c; return r;
+}
+__device__ __forceinline__ unsigned lcg_jump(unsigned x, unsigned long long steps) {
+  Affine acc = {1u, 0u};
+  Affine cur = {1103515245u, 12345u};
+  unsigned m = (unsigned)steps;   // the LCG has period 2^32
+  while (m) {
+    if (m & 1u) acc = compose(acc, cur);
+    cur = compose(cur, cur);
+    m >>= 1;
+  }
+  return acc.a * x + acc.c;
+}
+__device__ __forceinline__ int rand_r_dev(unsigned* seed) {
+  unsigned next = *seed, result;
+  next = next * 1103515245u + 12345u; result = (next >> 16) & 2047u;
+  next = next * 1103515245u + 12345u; result = (result << 10) ^ ((next >> 16) & 1023u);
+  next = next * 1103515245u + 12345u; result = (result << 10) ^ ((next >> 16) & 1023u);
+  *seed = next;
+  return (int)result;
+}
+
+// InitV (sgd_updater.cc:140-147) for the flagged keys; pos = exclusive scan of flags
+__global__ void k_initv(Table t, Params p, const int* __restrict__ slot, size_t n,
+                        const int* __restrict__ flags, const int* __restrict__ pos) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned long long vbase = t.state->n_vrows;
+  const unsigned seed0 = t.state->seed;
+  const int k = p.V_dim;
+  for (size_t i = warp0; i < n; i += nwarps) {
+    if (!flags[i]) continue;
+    const unsigned long long r = vbase + (unsigned long long)pos[i];
+    if (r >= t.vcap) { if (lane == 0) raise(t.prog, DFB_ERR_CAPACITY); continue; }
+    float* Vr = t.V + r * t.ks;
+    float* Cr = t.Vcg + r * t.ks;
+    for (int l = lane; l < t.ks; l += 32) {
+      float val = 0.f;
+      if (l < k) {
+        unsigned sd = lcg_jump(seed0, 3ULL * ((unsigned long long)pos[i] * k + l));
+        const int rr = rand_r_dev(&sd);
+        // (rand_r / (real_t)RAND_MAX - 0.5) * V_init_scale: float division, then double
+        const float u01 = __fdiv_rn((float)rr, 2147483648.0f);
+        val = __double2float_rn(__dmul_rn(__dsub_rn((double)u01, 0.5), (double)p.V_init_scale));
+      }
+      Vr[l] = val;
+      Cr[l] = 0.f;
+    }
+    if (lane == 0) t.tab[slot[i]].vrow = (int)r;
+  }
+}
+
+__global__ void k_initv_finalize(Table t, Params p, size_t n, const int* flags, const int* pos) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || n == 0) return;
+  const unsigned long long total = (unsigned long long)pos[n - 1] + (unsigned long long)flags[n - 1];
+  if (total == 0) return;
+  t.state->n_vrows += total;
+  t.state->seed = lcg_jump(t.state->seed, 3ULL * total * (unsigned long long)p.V_dim);
+  t.prog->new_vrows += total;
+}
+
+// ---- FTRL-proximal on w: SGDUpdater::UpdateW, sgd_updater.cc:104-127 ----
+// returns true when w went 0 -> nonzero (the InitV trigger :121-126)
+__device__ __forceinline__ bool ftrl_step(const Params& p, float gw, float& w, float& sqrt_g, float& z) {
+  const float sg = sqrt_g, w0 = w;
+  gw = __fadd_rn(gw, __fmul_rn(w0, p.l2));
+  sqrt_g = __fsqrt_rn(__fadd_rn(__fmul_rn(sg, sg), __fmul_rn(gw, gw)));
+  // z -= gw - (sqrt_g' - sg) / lr * w
+  z = __fsub_rn(z, __fsub_rn(gw, __fmul_rn(__fdiv_rn(__fsub_rn(sqrt_g, sg), p.lr), w0)));
+  const float l1 = p.l1;
+  if (z <= l1 && z >= -l1) {
+    w = 0.f;
+  } else {
+    const float eta = __fdiv_rn(__fadd_rn(p.lr_beta, sqrt_g), p.lr);
+    w = __fdiv_rn(z > 0.f ? __fsub_rn(z, l1) : __fadd_rn(z, l1), eta);
+  }
+  return w0 == 0.f && w != 0.f;
+}
+
+// ---- AdaGrad on one V component: SGDUpdater::UpdateV, sgd_updater.cc:129-138 ----
+__device__ __forceinline__ void adagrad_step(const Params& p, float gV, float& v, float& cg) {
+  const float g = __fadd_rn(gV, __fmul_rn(p.V_l2, v));
+  cg = __fsqrt_rn(__fadd_rn(__fmul_rn(cg, cg), __fmul_rn(g, g)));
+  const float eta = __fdiv_rn(p.V_lr, __fadd_rn(cg, p.V_lr_beta));
+  v = __fsub_rn(v, __fmul_rn(eta, g));
+}
+
+// penalty of one w (sgd_learner.cc:257 ; evaluated in fp32 here, double there)
+__device__ __forceinline__ float pen_w(const Params& p, float w) {
+  return p.l1 * fabsf(w) + 0.5f * p.l2 * w * w;
+}
+
+// fused scatter-finalize + FTRL + AdaGrad over dense per-key gradient rows.
+// One group of LPR lanes (float4 each) per key.
+template <int K>
+__global__ void __launch_bounds__(256) k_update_fast(Table t, Params p, const int* __restrict__ slot,
+                                                     const int* __restrict__ pull_vrow, int vrow_is_flag,
+                                                     size_t n, const float* __restrict__ gw,
+                                                     const float* __restrict__ gxxp,
+                                                     const float* __restrict__ gV, int* __restrict__ flags,
+                                                     int acc_pen) {
+  constexpr int LPR = K / 4;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  float pen = 0.f;
+  for (size_t base = warp0 * G; base < n; base += nwarps * G) {
+    const size_t i = base + grp;
+    if (i >= n) continue;
+    const int s = slot[i];
+    if (s < 0) { if (sub == 0) flags[i] = 0; continue; }
+    int vr = pull_vrow[i];
+    Entry* e = &t.tab[s];
+    if (vrow_is_flag && vr >= 0) vr = e->vrow;
+    const float g_w = gw[i];
+    if (sub == 0) {
+      float4 sc = *reinterpret_cast<const float4*>(&e->fea_cnt);   // {fea_cnt, w, sqrt_g, z}
+      if (acc_pen) pen += pen_w(p, sc.y);
+      const bool became_nz = ftrl_step(p, g_w, sc.y, sc.z, sc.w);
+      *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
+      flags[i] = (became_nz && p.V_dim > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
+    }
+    if (vr >= 0) {
+      const float xxp = gxxp ? gxxp[i] : g_w;
+      float* Vr = t.V + (size_t)vr * t.ks + sub * 4;
+      float* Cr = t.Vcg + (size_t)vr * t.ks + sub * 4;
+      float4 v = *reinterpret_cast<const float4*>(Vr);
+      float4 c = *reinterpret_cast<const float4*>(Cr);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gV + i * (size_t)t.ks + sub * 4));
+      if (acc_pen) pen += 0.5f * p.V_l2 * (v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+      // grad_V = sum_i x p XV_i  -  V * XXp   (fm_loss.h:181-198)
+      adagrad_step(p, __fsub_rn(g.x, __fmul_rn(v.x, xxp)), v.x, c.x);
+      adagrad_step(p, __fsub_rn(g.y, __fmul_rn(v.y, xxp)), v.y, c.y);
+      adagrad_step(p, __fsub_rn(g.z, __fmul_rn(v.z, xxp)), v.z, c.z);
+      adagrad_step(p, __fsub_rn(g.w, __fmul_rn(v.w, xxp)), v.w, c.w);
+      *reinterpret_cast<float4*>(Vr) = v;
+      *reinterpret_cast<float4*>(Cr) = c;
+    }
+  }
+  if (acc_pen) {
+    pen = warp_sum(pen);
+    if (lane == 0 && pen != 0.f) atomicAdd(&t.prog->penalty, (double)pen);
+  }
+}
+
+// any V_dim: one warp per key, dense gradient rows of stride ks
+__global__ void __launch_bounds__(256) k_update_dense_generic(Table t, Params p, const int* __restrict__ slot,
+                                                              const int* __restrict__ pull_vrow,
+                                                              int vrow_is_flag, size_t n,
+                                                              const float* __restrict__ gw,
+                                                              const float* __restrict__ gxxp,
+                                                              const float* __restrict__ gV,
+                                                              int* __restrict__ flags, int acc_pen) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int k = p.V_dim;
+  float pen = 0.f;
+  for (size_t i = warp0; i < n; i += nwarps) {
+    const int s = slot[i];
+    if (s < 0) { if (lane == 0) flags[i] = 0; continue; }
+    Entry* e = &t.tab[s];
+    int vr = k > 0 ? pull_vrow[i] : -1;
+    if (vrow_is_flag && vr >= 0) vr = e->vrow;
+    const float g_w = gw[i];
+    if (lane == 0) {
+      float4 sc = *reinterpret_cast<const float4*>(&e->fea_cnt);
+      if (acc_pen) pen += pen_w(p, sc.y);
+      const bool became_nz = ftrl_step(p, g_w, sc.y, sc.z, sc.w);
+      *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
+      flags[i] = (became_nz && k > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
+    }
+    if (vr >= 0) {
+      const float xxp = gxxp ? gxxp[i] : g_w;
+      float* Vr = t.V + (size_t)vr * t.ks;
+      float* Cr = t.Vcg + (size_t)vr * t.ks;
+      const float* g = gV + i * (size_t)t.ks;
+      for (int l = lane; l < k; l += 32) {
+        float v = Vr[l], c = Cr[l];
+        if (acc_pen) pen += 0.5f * p.V_l2 * v * v;
+        adagrad_step(p, __fsub_rn(g[l], __fmul_rn(v, xxp)), v, c);
+        Vr[l] = v; Cr[l] = c;
+      }
+    }
+  }
+  if (acc_pen) {
+    pen = warp_sum(pen);
+    if (lane == 0 && pen != 0.f) atomicAdd(&t.prog->penalty, (double)pen);
+  }
+}
+
+// the reference's ragged layout: grads = [gw_0,(gV_0..)][gw_1,...], lens[i] in {1, k+1}
+// (sgd_updater.cc:74-98).  lens == nullptr: w-only.
+__global__ void __launch_bounds__(256) k_update_ragged(Table t, Params p, const int* __restrict__ slot,
+                                                       size_t n, const float* __restrict__ grads,
+                                                       const int* __restrict__ lens,
+                                                       const int* __restrict__ pos, int* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int k = p.V_dim;
+  for (size_t i = warp0; i < n; i += nwarps) {
+    const int s = slot[i];
+    if (s < 0) { if (lane == 0) flags[i] = 0; continue; }
+    Entry* e = &t.tab[s];
+    const size_t off = lens ? (size_t)pos[i] : i;
+    const int len = lens ? lens[i] : 1;
+    const int vr = e->vrow;
+    if (lane == 0) {
+      float4 sc = *reinterpret_cast<const float4*>(&e->fea_cnt);
+      const bool became_nz = ftrl_step(p, grads[off], sc.y, sc.z, sc.w);
+      *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
+      flags[i] = (became_nz && k > 0 && vr < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
+    }
+    if (len > 1) {
+      // CHECK_EQ(lens[i], V_dim+1); CHECK(e.V != nullptr)  (sgd_updater.cc:92-93)
+      if (len != k + 1 || vr < 0) { if (lane == 0) raise(t.prog, DFB_ERR_INVALID); continue; }
+      float* Vr = t.V + (size_t)vr * t.ks;
+      float* Cr = t.Vcg + (size_t)vr * t.ks;
+      const float* g = grads + off + 1;
+      for (int l = lane; l < k; l += 32) {
+        float v = Vr[l], c = Cr[l];
+        adagrad_step(p, g[l], v, c);
+        Vr[l] = v; Cr[l] = c;
+      }
+    }
+  }
+}
+
+// penalty over pulled rows without updating (validation batches and the sharded worker;
+// sgd_learner.cc:249-273).  w_arr[i] is the pulled w; the V row is V + vrow[i]*ks, or
+// V + i*ks when dense (a pulled [n][ks] buffer with vrow[i] >= 0 meaning "present").
+__global__ void __launch_bounds__(256) k_penalty(Params p, DevProgress* prog, const float* __restrict__ w_arr,
+                                                 const int* __restrict__ vrow, const float* __restrict__ V,
+                                                 int ks, int dense, size_t n) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int k = p.V_dim;
+  float pen = 0.f;
+  for (size_t i = warp0; i < n; i += nwarps) {
+    if (lane == 0) pen += pen_w(p, w_arr[i]);
+    const int vr = k > 0 ? vrow[i] : -1;
+    if (vr >= 0) {
+      const float* Vr = V + (dense ? i : (size_t)vr) * (size_t)ks;
+      for (int l = lane; l < k; l += 32) pen += 0.5f * p.V_l2 * Vr[l] * Vr[l];
+    }
+  }
+  pen = warp_sum(pen);
+  if (lane == 0 && pen != 0.f) atomicAdd(&prog->penalty, (double)pen);
+}
+
+// w and vrow of already-located entries (the Pull of the fused path after a feature-count push)
+__global__ void k_pull_view(Table t, const int* __restrict__ slot, size_t n, float* __restrict__ w_out,
+                            int* __restrict__ vrow_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = slot[i];
+  w_out[i] = s >= 0 ? t.tab[s].w : 0.f;
+  vrow_out[i] = s >= 0 ? t.tab[s].vrow : -1;
+}
+
+// SGDUpdater::Get: lens (sgd_updater.cc:46-53)
+__global__ void k_lens(Table t, Params p, const int* __restrict__ slot, size_t n, int* __restrict__ lens) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = slot[i];
+  int len = 1;
+  if (p.V_dim > 0 && s >= 0 && t.tab[s].vrow >= 0) len = p.V_dim + 1;
+  lens[i] = len;
+}
+
+__global__ void k_pack_ragged(Table t, Params p, const int* __restrict__ slot, size_t n,
+                              const int* __restrict__ lens, const int* __restrict__ pos,
+                              float* __restrict__ vals, unsigned long long* nvals_out) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int k = p.V_dim;
+  for (size_t i = warp0; i < n; i += nwarps) {
+    const int s = slot[i];
+    const size_t off = (size_t)pos[i];
+    if (lane == 0) vals[off] = s >= 0 ? t.tab[s].w : 0.f;
+    if (lens[i] > 1) {
+      const float* Vr = t.V + (size_t)t.tab[s].vrow * t.ks;
+      for (int l = lane; l < k; l += 32) vals[off + 1 + l] = Vr[l];
+    }
+    if (i == n - 1 && lane == 0) *nvals_out = (unsigned long long)pos[i] + (unsigned long long)lens[i];
+  }
+}
+
+__global__ void k_gather_rows(Table t, const int* __restrict__ slot, size_t n, float* __restrict__ w_out,
+                              int* __restrict__ hasv_out, float* __restrict__ V_out) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t i = warp0; i < n; i += nwarps) {
+    const int s = slot[i];
+    const int vr = s >= 0 ? t.tab[s].vrow : -1;
+    if (lane == 0) {
+      w_out[i] = s >= 0 ? t.tab[s].w : 0.f;
+      hasv_out[i] = vr >= 0 ? 1 : -1;
+    }
+    if (vr >= 0 && V_out) {
+      const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vr * t.ks);
+      float4* dst = reinterpret_cast<float4*>(V_out + i * (size_t)t.ks);
+      for (int l = lane; l < t.ks / 4; l += 32) dst[l] = src[l];
+    }
+  }
+}
+
+__global__ void k_read_entries(Table t, const int* __restrict__ slot, size_t n, float* scal, int* hasv,
+                               float* V, float* cg, int k) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = slot[i];
+  if (s < 0) {
+    hasv[i] = -1;
+    for (int j = 0; j < 4; ++j) scal[i * 4 + j] = 0.f;
+    return;
+  }
+  const Entry e = t.tab[s];
+  scal[i * 4 + 0] = e.fea_cnt; scal[i * 4 + 1] = e.w; scal[i * 4 + 2] = e.sqrt_g; scal[i * 4 + 3] = e.z;
+  hasv[i] = e.vrow >= 0 ? 1 : 0;
+  if (e.vrow >= 0) {
+    for (int l = 0; l < k; ++l) {
+      if (V) V[i * (size_t)k + l] = t.V[(size_t)e.vrow * t.ks + l];
+      if (cg) cg[i * (size_t)k + l] = t.Vcg[(size_t)e.vrow * t.ks + l];
+    }
+  }
+}
+
+// Loss::Evaluate, loss.h:57-66
+__global__ void k_evaluate(const float* __restrict__ label, const float* __restrict__ pred, size_t n, double* out) {
+  __shared__ float red_s[32];
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float y = label[i] > 0.f ? 1.f : -1.f;
+    acc += logf(1.f + expf(-y * pred[i]));
+  }
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red_s[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    float v = lane < (int)(blockDim.x >> 5) ? red_s[lane] : 0.f;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(out, (double)v);
+  }
+}
+
+// BinClassMetric::AUC (bin_class_metric.h:35-56) on (pred ascending, label) pairs
+__global__ void __launch_bounds__(1024) k_auc_area(const float* __restrict__ sorted_label, size_t n, double* out_add) {
+  __shared__ unsigned long long s_tp[1024];
+  __shared__ unsigned long long s_area[1024];
+  const int tid = threadIdx.x;
+  const size_t per = (n + blockDim.x - 1) / blockDim.x;
+  const size_t b = (size_t)tid * per, e = b + per < n ? b + per : n;
+  unsigned long long tp = 0;
+  for (size_t i = b; i < e; ++i) tp += sorted_label[i] > 0.f ? 1 : 0;
+  s_tp[tid] = tp;
+  __syncthreads();
+  // exclusive prefix of positives before this thread's chunk (serial over 1024 in thread 0: tiny)
+  if (tid == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) { const unsigned long long c = s_tp[i]; s_tp[i] = run; run += c; }
+    s_area[0] = run;   // total positives, stashed
+  }
+  __syncthreads();
+  const unsigned long long total_tp = s_area[0];
+  __syncthreads();
+  unsigned long long cum = s_tp[tid], area = 0;
+  for (size_t i = b; i < e; ++i) {
+    if (sorted_label[i] > 0.f) cum += 1; else area += cum;
+  }
+  s_area[tid] = area;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long a = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) a += s_area[i];
+    double res;
+    if (total_tp == 0 || total_tp == n) {
+      res = 1.0;   // bin_class_metric.h:52
+    } else {
+      double ar = (double)a / ((double)total_tp * (double)(n - total_tp));
+      res = (ar < 0.5 ? 1.0 - ar : ar) * (double)n;
+    }
+    *out_add += res;
+  }
+}
+
+inline int grid_for(size_t n, int threads, int cap) {
+  size_t g = (n + threads - 1) / threads;
+  if (g == 0) g = 1;
+  return (int)(g < (size_t)cap ? g : (size_t)cap);
+}
+inline int grid_warps(size_t nwarps_needed, int warps_per_block, int cap) {
+  size_t g = (nwarps_needed + warps_per_block - 1) / warps_per_block;
+  if (g == 0) g = 1;
+  return (int)(g < (size_t)cap ? g : (size_t)cap);
+}
+
+}  // namespace
+
+int launch_table_init(Table& t, unsigned seed, cudaStream_t s) {
+  k_table_init<<<148 * 8, 256, 0, s>>>(t.tab, t.cap, t.state, t.prog, seed);
+  return 1;
+}
+
+int launch_lookup(Table& t, const uint64_t* keys, size_t n, bool insert, int* slot_out, float* w_out,
+                  int* vrow_out, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int threads = 256;
+  const int grid = (int)((n + threads - 1) / threads);
+  if (insert) k_lookup<true><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out);
+  else        k_lookup<false><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out);
+  return 1;
+}
+
+size_t scan_tmp_bytes(size_t n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (int)(n ? n : 1));
+  return bytes;
+}
+
+size_t sort_tmp_bytes(size_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const float*)nullptr, (float*)nullptr,
+                                  (const float*)nullptr, (float*)nullptr, (int)(n ? n : 1));
+  return bytes;
+}
+
+int launch_initv(Table& t, const Params& p, const int* slot, size_t n, int* flags, int* pos, void* cub_tmp,
+                 size_t cub_bytes, cudaStream_t s) {
+  if (n == 0 || p.V_dim == 0) return 0;
+  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, (int)n, s);
+  k_initv<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, p, slot, n, flags, pos);
+  k_initv_finalize<<<1, 32, 0, s>>>(t, p, n, flags, pos);
+  return 4;  // the CUB scan is 2 kernels
+}
+
+int launch_feacnt(Table& t, const Params& p, const int* slot, size_t n, const float* cnt, int* flags,
+                  int* pos, void* cub_tmp, size_t cub_bytes, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_feacnt<<<(int)((n + 255) / 256), 256, 0, s>>>(t, p, slot, n, cnt, flags);
+  return 1 + launch_initv(t, p, slot, n, flags, pos, cub_tmp, cub_bytes, s);
+}
+
+int launch_lens_scan(const int* lens, size_t n, int* pos, void* cub_tmp, size_t cub_bytes, cudaStream_t s) {
+  if (n == 0) return 0;
+  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, lens, pos, (int)n, s);
+  return 2;
+}
+
+int launch_pack_ragged(Table& t, const Params& p, const int* slot, size_t n, int* lens, int* pos, float* vals,
+                       unsigned long long* nvals_out, void* cub_tmp, size_t cub_bytes, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_lens<<<(int)((n + 255) / 256), 256, 0, s>>>(t, p, slot, n, lens);
+  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, lens, pos, (int)n, s);
+  k_pack_ragged<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, p, slot, n, lens, pos, vals, nvals_out);
+  return 4;
+}
+
+int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* hasv_out, float* V_out,
+                       cudaStream_t s) {
+  if (n == 0) return 0;
+  k_gather_rows<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, slot, n, w_out, hasv_out, V_out);
+  return 1;
+}
+
+int launch_update_dense(Table& t, const Params& p, const int* slot, const int* pull_vrow, int vrow_is_flag,
+                        size_t n, const float* gw, const float* gxxp, const float* gV, int* flags,
+                        int acc_pen, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int k = p.V_dim;
+#define DFB_UPD(K)                                                                                   \
+  k_update_fast<K><<<grid_warps((n + (32 / (K / 4)) - 1) / (32 / (K / 4)), 8, 148 * 8), 256, 0, s>>>( \
+      t, p, slot, pull_vrow, vrow_is_flag, n, gw, gxxp, gV, flags, acc_pen)
+  switch (k) {
+    case 8: DFB_UPD(8); return 1;
+    case 16: DFB_UPD(16); return 1;
+    case 32: DFB_UPD(32); return 1;
+    case 64: DFB_UPD(64); return 1;
+    case 128: DFB_UPD(128); return 1;
+    default: break;
+  }
+#undef DFB_UPD
+  k_update_dense_generic<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, p, slot, pull_vrow, vrow_is_flag, n, gw,
+                                                                  gxxp, gV, flags, acc_pen);
+  return 1;
+}
+
+int launch_update_ragged(Table& t, const Params& p, const int* slot, size_t n, const float* grads,
+                         const int* lens_or_null, const int* pos, int* flags, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_update_ragged<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, p, slot, n, grads, lens_or_null, pos, flags);
+  return 1;
+}
+
+int launch_penalty(const Params& p, DevProgress* prog, const float* w_arr, const int* vrow, const float* V,
+                   int ks, int dense, size_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_penalty<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(p, prog, w_arr, vrow, V, ks, dense, n);
+  return 1;
+}
+
+int launch_pull_view(Table& t, const int* slot, size_t n, float* w_out, int* vrow_out, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_pull_view<<<(int)((n + 255) / 256), 256, 0, s>>>(t, slot, n, w_out, vrow_out);
+  return 1;
+}
+
+int launch_evaluate(const float* label, const float* pred, size_t n, double* out, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_evaluate<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(label, pred, n, out);
+  return 1;
+}
+
+int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp, float* val_tmp,
+               float* key_tmp2, float* val_tmp2, void* cub_tmp, size_t cub_bytes, double* out_add,
+               cudaStream_t s) {
+  (void)key_tmp; (void)val_tmp;
+  if (n == 0) return 0;
+  // stable ascending radix sort by pred: ties keep original row order
+  cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, pred, key_tmp2, label, val_tmp2, (int)n, 0, 32, s);
+  k_auc_area<<<1, 1024, 0, s>>>(val_tmp2, n, out_add);
+  return 4;
+}
+
+int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* hasv, float* V, float* cg,
+                        int k, cudaStream_t s) {
+  if (n == 0) return 0;
+  k_read_entries<<<(int)((n + 127) / 128), 128, 0, s>>>(t, slot, n, scal, hasv, V, cg, k);
+  return 1;
+}
+
+}  // namespace dfb

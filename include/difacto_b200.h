@@ -1,0 +1,214 @@
+/*
+ * include/difacto_b200.h -- the drop-in boundary of difacto-b200.
+ *
+ * A C-ABI (plain pointers and sizes, no C++/torch types) over the B200-native
+ * FM-SGD engine.  Each entry point replaces one interface of the reference
+ * (dmlc/difacto @ 78e3562; paths below are relative to that tree).  The reference
+ * itself has no C ABI on this path -- it has four C++ abstract classes
+ * (include/difacto/{loss,updater,store,learner}.h); INTEGRATION.md shows the
+ * adapter classes a maintainer adds there to bind these symbols.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative dfb_status; the message is
+ *    available from dfb_last_error(h).  Nothing aborts the process (the reference
+ *    CHECK()s -> abort(), Makefile:13 -DDMLC_LOG_FATAL_THROW=0; the C++ adapter maps a
+ *    non-zero code back to LOG(FATAL)).
+ *  - a handle owns one CUDA device, one compute stream and one copy stream.  It is
+ *    thread-compatible: at most one call in flight per handle (the reference's Loss is
+ *    not re-entrant either: fm_loss.h:202-203 member state).
+ *  - "host" pointers are ordinary host memory (pinned memory from dfb_host_alloc makes
+ *    the copies asynchronous); "dev" pointers are device memory on the handle's device.
+ *  - feature keys are the reference's *reversed* feature ids (ReverseBytes,
+ *    include/difacto/base.h:39-51), sorted ascending and unique, exactly what
+ *    Localizer::Compact emits (src/data/localizer.cc:36-49).
+ *  - all floating point is fp32 (real_t, include/difacto/base.h:16).
+ */
+#ifndef DIFACTO_B200_H_
+#define DIFACTO_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dfb_engine* dfb_handle;
+
+typedef enum {
+  DFB_OK = 0,
+  DFB_ERR_INVALID = -1,   /* bad argument / a CHECK of the reference would have fired */
+  DFB_ERR_CUDA = -2,      /* CUDA runtime error */
+  DFB_ERR_CAPACITY = -3,  /* key table or V-row pool exhausted */
+  DFB_ERR_PARAM = -4,     /* parameter missing / out of range (dmlc::ParamError in the reference) */
+  DFB_ERR_NCCL = -5
+} dfb_status;
+
+/* value types of Store::Push / Pull: include/difacto/store.h:33-35 */
+enum { DFB_FEA_COUNT = 1, DFB_WEIGHT = 2, DFB_GRADIENT = 3 };
+
+/* sgd::Progress, src/sgd/sgd_utils.h:40-45 (+ device-side counters) */
+typedef struct {
+  float loss;      /* sum_i log(1+exp(-y_i pred_i))            loss.h:57-66            */
+  float penalty;   /* l1|w| + .5 l2 w^2 + .5 V_l2 V^2 (pulled)  sgd_learner.cc:249-273  */
+  float auc;       /* AUC * nrows                               bin_class_metric.h:35-56 */
+  float nnz_w;     /* unused by the SGD learner (kept for layout compatibility)          */
+  float nrows;
+  /* extras (not in the reference) */
+  uint64_t new_keys;    /* keys inserted by this step                 */
+  uint64_t new_vrows;   /* V rows allocated (InitV) by this step      */
+} dfb_progress;
+
+/* ---------------------------------------------------------------------------------
+ * life cycle.  Replaces SGDUpdater::Init (src/sgd/sgd_updater.cc:9-11) + FMLoss::Init
+ * (src/loss/fm_loss.h:37-39) + Store::Init.  Consumes the reference's SGDUpdaterParam
+ * keys with the same names, defaults and ranges (src/sgd/sgd_param.h:66-107):
+ *   l1 l2 V_l2 lr lr_beta V_lr V_lr_beta V_init_scale V_dim V_threshold seed
+ * plus engine-only keys (unknown to the reference, ignored by it with a warning):
+ *   device (0)            CUDA device ordinal
+ *   table_capacity (1<<20) max number of distinct keys this shard can hold
+ *   V_capacity (=table_capacity) max number of keys with an allocated V row
+ *   max_batch_nnz / max_batch_rows / max_batch_keys   workspace sizing hints (grow on demand)
+ *   compute_auc (1)       evaluate AUC on device each step (sgd_learner.cc:150-153)
+ *   deterministic (0)     1 = gradient scatter through a sorted segmented reduction
+ *                         (bit-reproducible); 0 = fp32 red.global atomics
+ * Keys that are neither are returned through dfb_unknown_kwarg, mirroring the
+ * "return the unconsumed kwargs" convention (updater.h:34, main.cc:25-31).
+ * ------------------------------------------------------------------------------- */
+int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_handle* out);
+int dfb_destroy(dfb_handle h);
+const char* dfb_last_error(dfb_handle h);   /* h may be NULL: error of the failed dfb_create */
+int dfb_num_unknown_kwargs(dfb_handle h);
+int dfb_unknown_kwarg(dfb_handle h, int i, const char** key, const char** val);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+uint64_t dfb_launch_count(dfb_handle h);
+/* number of keys / V rows currently stored */
+int dfb_table_stats(dfb_handle h, uint64_t* n_keys, uint64_t* n_vrows, uint64_t* capacity,
+                    uint64_t* v_capacity);
+
+/* pinned host memory so that H2D/D2H copies are asynchronous DMA */
+int dfb_host_alloc(void** ptr, size_t bytes);
+int dfb_host_free(void* ptr);
+
+/* ---------------------------------------------------------------------------------
+ * (A) API-faithful path: host buffers in, host buffers out; one call = one reference
+ * call.  Used by the adapter classes GpuStore/GpuSGDUpdater/GpuFMLoss.
+ * ------------------------------------------------------------------------------- */
+
+/* Store::Push(keys, kFeaCount, cnt)  store_local.h:24-34 -> SGDUpdater::Update
+ * sgd_updater.cc:62-73: fea_cnt += cnt; allocate V when w!=0 && fea_cnt>V_threshold. */
+int dfb_push_feacnt(dfb_handle h, const uint64_t* keys, size_t n, const float* cnt);
+
+/* Store::Pull(keys, kWeight, &vals, &lens)  store_local.h:36-44 -> SGDUpdater::Get
+ * sgd_updater.cc:32-56.  vals_out (capacity vals_cap floats, n*(1+V_dim) always suffices)
+ * receives the ragged [w_i, V_i...] rows; lens_out[n] receives 1 or 1+V_dim;
+ * *nlens = 0 when V_dim == 0 (sgd_updater.cc:40), n otherwise. */
+int dfb_pull(dfb_handle h, const uint64_t* keys, size_t n, float* vals_out, size_t vals_cap,
+             int* lens_out, size_t* nvals, size_t* nlens);
+
+/* Store::Push(keys, kGradient, grads, lens) -> SGDUpdater::Update sgd_updater.cc:74-101:
+ * FTRL on w (UpdateW :104-127), AdaGrad on V (UpdateV :129-138), lazy InitV (:140-147).
+ * nlens == 0 means w-only (lens.empty()). */
+int dfb_push_grad(dfb_handle h, const uint64_t* keys, size_t n, const float* grads,
+                  size_t nvals, const int* lens, size_t nlens);
+
+/* FMLoss::Predict  src/loss/fm_loss.h:67-119.  CSR<u32> data (dmlc::RowBlock<unsigned>:
+ * offset[nrows+1] of size_t, index, optional value), weights in the pulled ragged layout
+ * with w_pos/V_pos (-1 = absent; both NULL = direct indexing, the V_dim==0 path).
+ * pred[nrows] is ACCUMULATED into, as in the reference (caller zero-fills). */
+int dfb_predict(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index,
+                const float* value_or_null, const float* weights, size_t nweights,
+                const int* w_pos, const int* V_pos, size_t npos, float* pred);
+
+/* FMLoss::CalcGrad  src/loss/fm_loss.h:148-199.  grad[nweights] (same ragged layout as
+ * weights) is ACCUMULATED into.  Unlike the reference it does not depend on member state
+ * left behind by Predict (XV_ is recomputed on device). */
+int dfb_calc_grad(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index,
+                  const float* value_or_null, const float* label, const float* weights,
+                  size_t nweights, const int* w_pos, const int* V_pos, size_t npos,
+                  const float* pred, float* grad);
+
+/* Loss::Evaluate  include/difacto/loss.h:57-66 */
+int dfb_evaluate(dfb_handle h, const float* label, const float* pred, size_t n, float* objv);
+
+/* BinClassMetric::AUC  src/loss/bin_class_metric.h:35-56 (returns AUC * n; ties keep row order) */
+int dfb_auc(dfb_handle h, const float* label, const float* pred, size_t n, float* auc_times_n);
+
+/* ---------------------------------------------------------------------------------
+ * (B) fused device-resident step: replaces the whole pull_callback of
+ * SGDLearner::IterateData (src/sgd/sgd_learner.cc:138-177 + the kFeaCount push :214-217):
+ *   [fea_cnt push] -> Pull -> GetPos -> Predict -> Evaluate -> penalty -> AUC ->
+ *   [CalcGrad -> Push(kGradient)]
+ * on a batch already localized by Localizer::Compact (CSR<u32> + sorted unique reversed
+ * keys [+ counts]).  The table never leaves HBM; the host sees only dfb_progress.
+ * cnt_or_null != NULL reproduces the epoch-0 feature-count push; is_train == 0 is a
+ * validation batch (no CalcGrad/Push, sgd_learner.cc:158-171).
+ * pred_out_or_null receives the nrows clamped predictions if not NULL.
+ * ------------------------------------------------------------------------------- */
+int dfb_train_step(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index,
+                   const float* value_or_null, const float* label, const uint64_t* keys,
+                   size_t nkeys, const float* cnt_or_null, int is_train, dfb_progress* out,
+                   float* pred_out_or_null);
+
+/* same, but every array is already resident in device memory on the handle's device and
+ * the call only enqueues work on the handle's stream (no host synchronisation);
+ * dfb_sync() / dfb_read_progress() collect the result. */
+int dfb_train_step_dev(dfb_handle h, size_t nrows, const uint64_t* d_offset,
+                       const uint32_t* d_index, const float* d_value_or_null,
+                       const float* d_label, const uint64_t* d_keys, size_t nkeys,
+                       const float* d_cnt_or_null, int is_train);
+int dfb_sync(dfb_handle h);
+/* blocks until enqueued steps are done; returns the Progress ACCUMULATED since the last
+ * read (the reference merges per-batch Progress by addition, sgd_utils.h:66-71) */
+int dfb_read_progress(dfb_handle h, dfb_progress* out);
+
+/* pipelined host-buffer variant: enqueue H2D (from pinned memory: truly asynchronous)
+ * + the step, double-buffered so that the copy of batch t+1 overlaps the compute of
+ * batch t (the reference keeps <=2 batches in flight, sgd_learner.cc:220-223). */
+int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset,
+                         const uint32_t* index, const float* value_or_null, const float* label,
+                         const uint64_t* keys, size_t nkeys, const float* cnt_or_null,
+                         int is_train);
+
+/* ---------------------------------------------------------------------------------
+ * model inspection (tests, checkpointing): read entries of the table.
+ * scal_out[n][4] = {fea_cnt, w, sqrt_g, z} (SGDEntry, sgd_updater.h:19-29),
+ * has_V_out[n] in {-1 absent, 0 no V, 1 V}; V_out/cg_out [n][V_dim] (may be NULL).
+ * ------------------------------------------------------------------------------- */
+int dfb_read_entries(dfb_handle h, const uint64_t* keys, size_t n, float* scal_out,
+                     int* has_V_out, float* V_out, float* cg_out);
+/* state of the InitV random stream (SGDUpdaterParam::seed after the rand_r calls so far) */
+int dfb_rng_state(dfb_handle h, uint32_t* seed);
+
+/* ---------------------------------------------------------------------------------
+ * key-range sharding (multi-GPU).  ps-lite Postoffice::GetServerKeyRanges
+ * (ps-lite/src/postoffice.cc:127-136) + KVWorker::DefaultSlicer (kv_app.h:406-460):
+ * shard i owns reversed keys in [UINT64_MAX/S*i, UINT64_MAX/S*(i+1)); the tail above
+ * UINT64_MAX/S*S is clamped into shard S-1.  Because keys are sorted, every shard's keys
+ * are one contiguous segment: bounds_out[S+1] are the segment boundaries.
+ * ------------------------------------------------------------------------------- */
+uint32_t dfb_key_owner(uint64_t reversed_key, uint32_t num_shards);
+int dfb_shard_bounds(const uint64_t* sorted_keys, size_t n, uint32_t num_shards,
+                     size_t* bounds_out);
+
+/* device-side building blocks for the sharded store (all pointers are device memory,
+ * work is enqueued on the handle's stream; see difacto_b200/sharded.py for the protocol):
+ *   owner side of Pull:  keys -> rows {w, has_V, V[ks]} packed for the all-to-all
+ *   owner side of Push:  received {gw, gxxp, gV[ks]} rows applied with FTRL/AdaGrad
+ *   worker side:         FM forward/backward on a pulled dense buffer               */
+int dfb_row_stride(dfb_handle h);  /* ks: V_dim rounded up to a multiple of 4 floats */
+int dfb_dev_feacnt(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_cnt);
+int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w_out,
+                      int* d_hasv_out, float* d_V_out);
+int dfb_dev_fm_step(dfb_handle h, size_t nrows, const uint64_t* d_offset,
+                    const uint32_t* d_index, const float* d_value_or_null, const float* d_label,
+                    size_t nkeys, const float* d_w, const int* d_hasv, const float* d_V,
+                    int is_train, float* d_gw_out, float* d_gxxp_out, float* d_gV_out);
+int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_gw,
+                      const float* d_gxxp, const int* d_hasv, const float* d_gV);
+/* the CUDA stream (cudaStream_t) the handle enqueues on, for event interop with torch */
+void* dfb_stream(dfb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DIFACTO_B200_H_ */
