@@ -31,6 +31,7 @@ EXPORTS = [
     "dfb_train_step", "dfb_train_step_dev", "dfb_sync", "dfb_read_progress", "dfb_train_step_async",
     "dfb_read_entries", "dfb_rng_state", "dfb_key_owner", "dfb_shard_bounds", "dfb_row_stride",
     "dfb_dev_feacnt", "dfb_dev_pull_rows", "dfb_dev_fm_step", "dfb_dev_push_rows", "dfb_stream",
+    "dfb_wait_step", "dfb_profile", "dfb_profile_read",
 ]
 
 _LIB = None
@@ -63,7 +64,7 @@ def lib():
         L.dfb_evaluate.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_float)]
         L.dfb_auc.argtypes = [vp, vp, vp, sz, C.POINTER(C.c_float)]
         L.dfb_train_step.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, C.c_int, C.POINTER(Progress), vp]
-        L.dfb_train_step_dev.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, C.c_int]
+        L.dfb_train_step_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, vp, sz, vp, C.c_int]
         L.dfb_train_step_async.argtypes = [vp, sz, vp, vp, vp, vp, vp, sz, vp, C.c_int]
         L.dfb_sync.argtypes = [vp]
         L.dfb_read_progress.argtypes = [vp, C.POINTER(Progress)]
@@ -75,8 +76,11 @@ def lib():
         L.dfb_row_stride.argtypes = [vp]
         L.dfb_dev_feacnt.argtypes = [vp, vp, sz, vp]
         L.dfb_dev_pull_rows.argtypes = [vp, vp, sz, vp, vp, vp]
-        L.dfb_dev_fm_step.argtypes = [vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp, vp]
+        L.dfb_dev_fm_step.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp, vp]
         L.dfb_dev_push_rows.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+        L.dfb_wait_step.argtypes = [vp, C.POINTER(Progress)]
+        L.dfb_profile.argtypes = [vp, C.c_int]
+        L.dfb_profile_read.argtypes = [vp, vp, vp]
         L.dfb_stream.restype = vp
         L.dfb_stream.argtypes = [vp]
         _LIB = L
@@ -244,12 +248,28 @@ class Engine:
         self._ck(self.L.dfb_train_step_async(self.h, nrows, _p(offset), _p(lidx), _p(value), _p(label),
                                              _p(keys), nkeys, _p(cnt), int(is_train)))
 
-    def train_step_dev(self, nrows, d_offset, d_lidx, d_value, d_label, d_keys, nkeys, d_cnt=None, is_train=True):
-        self._ck(self.L.dfb_train_step_dev(self.h, nrows, _p(d_offset), _p(d_lidx), _p(d_value), _p(d_label),
-                                           _p(d_keys), nkeys, _p(d_cnt), int(is_train)))
+    def train_step_dev(self, nrows, nnz, d_offset, d_lidx, d_value, d_label, d_keys, nkeys, d_cnt=None,
+                       is_train=True):
+        self._ck(self.L.dfb_train_step_dev(self.h, nrows, nnz, _p(d_offset), _p(d_lidx), _p(d_value),
+                                           _p(d_label), _p(d_keys), nkeys, _p(d_cnt), int(is_train)))
 
     def sync(self):
         self._ck(self.L.dfb_sync(self.h))
+
+    def wait_step(self):
+        pr = Progress()
+        self._ck(self.L.dfb_wait_step(self.h, C.byref(pr)))
+        return pr
+
+    def profile(self, enable=True):
+        self._ck(self.L.dfb_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        ms = np.zeros(4, np.float64)
+        cnt = np.zeros(4, np.uint64)
+        self._ck(self.L.dfb_profile_read(self.h, _p(ms), _p(cnt)))
+        names = ["lookup", "fm", "auc", "update"]
+        return {n: dict(ms=float(ms[i]), count=int(cnt[i])) for i, n in enumerate(names)}
 
     def read_progress(self):
         pr = Progress()
@@ -273,8 +293,9 @@ class Engine:
     def dev_pull_rows(self, d_keys, n, d_w, d_hasv, d_V):
         self._ck(self.L.dfb_dev_pull_rows(self.h, _p(d_keys), n, _p(d_w), _p(d_hasv), _p(d_V)))
 
-    def dev_fm_step(self, nrows, d_off, d_idx, d_val, d_lab, nkeys, d_w, d_hasv, d_V, is_train, d_gw, d_gxxp, d_gV):
-        self._ck(self.L.dfb_dev_fm_step(self.h, nrows, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys, _p(d_w),
+    def dev_fm_step(self, nrows, nnz, d_off, d_idx, d_val, d_lab, nkeys, d_w, d_hasv, d_V, is_train, d_gw, d_gxxp,
+                    d_gV):
+        self._ck(self.L.dfb_dev_fm_step(self.h, nrows, nnz, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys, _p(d_w),
                                         _p(d_hasv), _p(d_V), int(is_train), _p(d_gw), _p(d_gxxp), _p(d_gV)))
 
     def dev_push_rows(self, d_keys, n, d_gw, d_gxxp, d_hasv, d_gV):

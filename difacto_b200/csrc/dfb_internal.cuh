@@ -4,8 +4,10 @@
 //   Entry tab[cap]        32-byte open-addressing hash entries, one DRAM sector each:
 //                         {u64 reversed key, i32 vrow, i32 pad, f32 fea_cnt, w, sqrt_g, z}
 //                         == the reference's unordered_map<feaid_t,SGDEntry> (sgd_updater.h:19-29,84)
-//   float V  [vcap][ks]   embedding rows, ks = V_dim rounded up to 4 floats (16-byte rows)
-//   float Vcg[vcap][ks]   AdaGrad accumulators (the second half of SGDEntry::V, sgd_updater.cc:142)
+//   float VV[vcap][2*ks]  one row per key with an embedding: [V (ks) | AdaGrad accumulators (ks)],
+//                         ks = V_dim rounded up to 4 floats -- the reference's `new real_t[2n]`
+//                         (sgd_updater.cc:142).  The gather reads the first half (one contiguous
+//                         4k-byte chunk); the update reads and writes the whole 8k-byte row.
 // V rows are allocated lazily from a bump pool, exactly when the reference calls InitV.
 #pragma once
 #include <cuda_runtime.h>
@@ -52,7 +54,8 @@ struct Table {
   float* V = nullptr;
   float* Vcg = nullptr;
   uint64_t vcap = 0;
-  int ks = 0;  // row stride in floats
+  int ks = 0;  // V_dim rounded up to a multiple of 4 floats
+  int rs = 0;  // stride between table rows in floats (2*ks); Vcg == V + ks
   TableState* state = nullptr;
   DevProgress* prog = nullptr;
 };
@@ -89,7 +92,16 @@ struct FmBatch {
   int V_dim;
   int train;
   DevProgress* prog;        // loss / nrows accumulated here when non-null
+  // emit mode (train && emit): instead of scattering with atomics the kernel writes
+  int emit;
+  float* p_out;             //   p_i = -y/(1+exp(y pred_i))            [nrows]
+  float* pxv_out;           //   p_i * XV_i                             [nrows][V_dim]
+  uint32_t* occ_row;        //   row of every nnz (binary data)         [nnz]
+  unsigned long long* occ_rowx;  // (row << 32 | bits(x)) (valued data) [nnz]
 };
+
+// true when launch_fm would take the 16-byte-lane fast path for this V_dim / view
+bool fm_fast_supported(int V_dim);
 
 // ---- launchers (kernels_fm.cu) ----
 // returns number of kernel launches performed, or <0 on invalid configuration
@@ -141,5 +153,23 @@ int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp, 
                cudaStream_t s);
 int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* hasv, float* V,
                         float* cg, int k, cudaStream_t s);
+
+// ---- sorted (atomic-free, deterministic) gradient reduction ----
+// CSC view of the batch: stable radix sort of (local key id -> occurrence payload); afterwards
+// key u owns occ_sorted[col_start[u] .. col_end[u]) in row order (the reference's summation
+// order per column, spmm.h:140-156).
+size_t csc_tmp_bytes(size_t nnz, bool valued);
+int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t nnz, size_t nkeys,
+                     uint32_t* lidx_sorted, void* occ_sorted, int* col_start, int* col_end,
+                     void* cub_tmp, size_t cub_bytes, cudaStream_t s);
+// per key: grad = sum_occ x * pXV[row] - V * XXp, then either FTRL/AdaGrad in place (apply) or
+// dense gradient rows out (gw_out/gxxp_out/gV_out, the sharded worker).
+int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,
+                      const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
+                      const float* p_row, const float* pxv, int* flags, int accumulate_penalty,
+                      cudaStream_t s);
+int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* col_start,
+                     const int* col_end, const void* occ_sorted, bool valued, const float* p_row,
+                     const float* pxv, float* gw_out, float* gxxp_out, float* gV_out, cudaStream_t s);
 
 }  // namespace dfb

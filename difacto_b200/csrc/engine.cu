@@ -37,6 +37,7 @@ struct dfb_engine {
   int device = 0;
   int compute_auc = 1;
   int force_generic = 0;
+  int scatter_sorted = 1;   // 1: atomic-free sorted reduction (deterministic); 0: red.global atomics
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   Table tab;
   std::string err;
@@ -46,11 +47,27 @@ struct dfb_engine {
   // workspaces (grown on demand)
   DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
   DevBuf auc_k, auc_v;
+  DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
   DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
   DevBuf scal, hasv, rV, rcg, nvals;
   // double-buffered inputs of the pipelined step
   struct InSet { DevBuf off, idx, val, lab, keys, cnt; cudaEvent_t copied = nullptr, consumed = nullptr; } in[2];
   uint64_t seq = 0;
+  // per-step Progress snapshots of the pipelined path (pinned ring + completion events)
+  static constexpr int kRing = 4;
+  DevProgress* h_ring = nullptr;
+  cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t submitted = 0, collected = 0;
+  DevProgress backlog;             // snapshots folded in when the ring was full
+  // optional per-stage CUDA-event timing (bench.py's roofline numbers)
+  static constexpr int kStages = 4;      // lookup+pull, fm, auc, update(+initv)
+  static constexpr int kProfRing = 32;
+  int profile = 0;
+  std::vector<cudaEvent_t> pev;          // [kProfRing][kStages][2]
+  std::vector<char> pev_used;            // [kProfRing][kStages]
+  uint64_t prof_steps = 0;
+  double stage_ms[kStages] = {0, 0, 0, 0};
+  uint64_t stage_n[kStages] = {0, 0, 0, 0};
   DevProgress* h_prog = nullptr;   // pinned
   unsigned long long* h_nvals = nullptr;  // pinned
 
@@ -182,10 +199,68 @@ int h2d(dfb_engine* h, DevBuf& b, const void* src, size_t bytes, cudaStream_t s)
   return 0;
 }
 
+void add_prog(DevProgress& a, const DevProgress& b) {
+  a.loss += b.loss; a.penalty += b.penalty; a.auc += b.auc;
+  a.nrows += b.nrows; a.new_keys += b.new_keys; a.new_vrows += b.new_vrows;
+  if (a.err == 0) a.err = b.err;
+}
+
+void to_public(const DevProgress& d, dfb_progress* out) {
+  out->loss = (float)d.loss; out->penalty = (float)d.penalty; out->auc = (float)d.auc;
+  out->nnz_w = 0.f; out->nrows = (float)d.nrows; out->new_keys = d.new_keys; out->new_vrows = d.new_vrows;
+}
+
+int prof_drain(dfb_engine* h) {
+  if (h->pev.empty()) return 0;
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < dfb_engine::kProfRing; ++r)
+    for (int st = 0; st < dfb_engine::kStages; ++st) {
+      char& used = h->pev_used[r * dfb_engine::kStages + st];
+      if (!used) continue;
+      float ms = 0.f;
+      cudaEvent_t* e = &h->pev[(r * dfb_engine::kStages + st) * 2];
+      if (cudaEventElapsedTime(&ms, e[0], e[1]) == cudaSuccess) { h->stage_ms[st] += ms; h->stage_n[st]++; }
+      used = 0;
+    }
+  return 0;
+}
+
+struct StageTimer {
+  dfb_engine* h; int st; cudaEvent_t* e = nullptr;
+  StageTimer(dfb_engine* h_, int st_) : h(h_), st(st_) {
+    if (!h->profile) return;
+    const int r = (int)(h->prof_steps % dfb_engine::kProfRing);
+    e = &h->pev[(r * dfb_engine::kStages + st) * 2];
+    cudaEventRecord(e[0], h->stream);
+  }
+  ~StageTimer() {
+    if (!e) return;
+    cudaEventRecord(e[1], h->stream);
+    h->pev_used[((h->prof_steps % dfb_engine::kProfRing)) * dfb_engine::kStages + st] = 1;
+  }
+};
+
 // the fused minibatch on device-resident inputs (everything enqueued on h->stream)
-int step_dev(dfb_engine* h, size_t nrows, const uint64_t* d_off, const uint32_t* d_idx, const float* d_val,
-             const float* d_lab, const uint64_t* d_keys, size_t U, const float* d_cnt, int is_train) {
-  if (U > 0x7fffffffULL || nrows > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "batch too large");
+int ensure_sorted_ws(dfb_engine* h, size_t nrows, size_t nnz, size_t U, bool valued) {
+  const int k = h->prm.V_dim;
+  DFB_TRY(h->ensure(h->pxv, nrows * (size_t)k * sizeof(float)));
+  DFB_TRY(h->ensure(h->p_row, nrows * sizeof(float)));
+  DFB_TRY(h->ensure(h->occ, nnz * (valued ? 8 : 4)));
+  DFB_TRY(h->ensure(h->occ_sorted, nnz * (valued ? 8 : 4)));
+  DFB_TRY(h->ensure(h->lidx_sorted, nnz * sizeof(uint32_t)));
+  DFB_TRY(h->ensure(h->col_start, U * sizeof(int)));
+  DFB_TRY(h->ensure(h->col_end, U * sizeof(int)));
+  const size_t cb = csc_tmp_bytes(nnz, valued);
+  if (cb > h->cub.bytes) DFB_TRY(h->ensure(h->cub, cb));
+  return 0;
+}
+
+int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint32_t* d_idx,
+             const float* d_val, const float* d_lab, const uint64_t* d_keys, size_t U, const float* d_cnt,
+             int is_train) {
+  if (U > 0x7fffffffULL || nrows > 0x7fffffffULL || nnz > 0x7fffffffULL)
+    return h->fail(DFB_ERR_INVALID, "batch too large");
+  const bool sorted = is_train && h->scatter_sorted && !h->force_generic && fm_fast_supported(h->prm.V_dim);
   const int ks = h->tab.ks;
   cudaStream_t s = h->stream;
   DFB_TRY(ensure_key_ws(h, U));
@@ -195,7 +270,10 @@ int step_dev(dfb_engine* h, size_t nrows, const uint64_t* d_off, const uint32_t*
   int* u_vrow = h->u_vrow.as<int>();
   int* flags = h->flags.as<int>();
   int* pos = h->pos.as<int>();
+  if (h->profile && h->prof_steps && h->prof_steps % dfb_engine::kProfRing == 0) DFB_TRY(prof_drain(h));
   // Push(kFeaCount) then Pull (sgd_learner.cc:214-217, :177)
+  {
+  StageTimer tm(h, 0);
   if (d_cnt) {
     h->launches += launch_lookup(h->tab, d_keys, U, true, slot, nullptr, nullptr, s);
     h->launches += launch_feacnt(h->tab, h->prm, slot, U, d_cnt, flags, pos, h->cub.p, h->cub.bytes, s);
@@ -203,11 +281,14 @@ int step_dev(dfb_engine* h, size_t nrows, const uint64_t* d_off, const uint32_t*
   } else {
     h->launches += launch_lookup(h->tab, d_keys, U, true, slot, u_w, u_vrow, s);
   }
+  }
   FmView v;
   memset(&v, 0, sizeof(v));
   v.wbase = u_w; v.w_pos = nullptr;
-  v.vbase = h->tab.V; v.v_pos = u_vrow; v.vstride = ks; v.dense = 0;
-  if (is_train) {
+  v.vbase = h->tab.V; v.v_pos = u_vrow; v.vstride = h->tab.rs; v.dense = 0;
+  if (sorted) {
+    DFB_TRY(ensure_sorted_ws(h, nrows, nnz, U, d_val != nullptr));
+  } else if (is_train) {
     DFB_TRY(h->ensure(h->gw, U * sizeof(float)));
     DFB_CUDA(h, cudaMemsetAsync(h->gw.p, 0, U * sizeof(float), s));
     if (h->prm.V_dim > 0) {
@@ -227,7 +308,12 @@ int step_dev(dfb_engine* h, size_t nrows, const uint64_t* d_off, const uint32_t*
   b.nrows = nrows; b.offset = d_off; b.index = d_idx; b.value = d_val; b.label = d_lab;
   b.pred_in = nullptr; b.pred_io = h->pred.as<float>(); b.pred_acc = 0;
   b.V_dim = h->prm.V_dim; b.train = is_train; b.prog = h->tab.prog;
+  if (sorted) {
+    b.emit = 1; b.p_out = h->p_row.as<float>(); b.pxv_out = h->pxv.as<float>();
+    b.occ_row = h->occ.as<uint32_t>(); b.occ_rowx = h->occ.as<unsigned long long>();
+  }
   if (nrows) {
+    StageTimer tm(h, 1);
     int nl = launch_fm(b, v, h->force_generic, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
     h->launches += nl;
@@ -237,18 +323,45 @@ int step_dev(dfb_engine* h, size_t nrows, const uint64_t* d_off, const uint32_t*
     DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
     size_t sb = sort_tmp_bytes(nrows);
     if (sb > h->cub.bytes) DFB_TRY(h->ensure(h->cub, sb));
+    StageTimer tm(h, 2);
     h->launches += launch_auc(d_lab, h->pred.as<float>(), nrows, nullptr, nullptr, h->auc_k.as<float>(),
                               h->auc_v.as<float>(), h->cub.p, h->cub.bytes, &h->tab.prog->auc, s);
   }
-  if (is_train) {
+  StageTimer tm_upd(h, 3);
+  if (sorted) {
+    // CalcGrad + Push(kGradient) without materialising the gradient: CSC view of the batch, then
+    // per key reduce + FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
+    h->launches += launch_csc_build(d_idx, h->occ.p, d_val != nullptr, nnz, U, h->lidx_sorted.as<uint32_t>(),
+                                    h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
+                                    h->cub.bytes, s);
+    int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U, h->col_start.as<int>(), h->col_end.as<int>(),
+                               h->occ_sorted.p, d_val != nullptr, h->p_row.as<float>(), h->pxv.as<float>(), flags,
+                               1, s);
+    if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
+    h->launches += nl;
+    h->launches += launch_initv(h->tab, h->prm, slot, U, flags, pos, h->cub.p, h->cub.bytes, s);
+  } else if (is_train) {
     // Push(kGradient): FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
     h->launches += launch_update_dense(h->tab, h->prm, slot, u_vrow, 0, U, h->gw.as<float>(),
                                        d_val ? h->gxxp.as<float>() : nullptr, h->gV.as<float>(), flags, 1, s);
     h->launches += launch_initv(h->tab, h->prm, slot, U, flags, pos, h->cub.p, h->cub.bytes, s);
   } else {
-    h->launches += launch_penalty(h->prm, h->tab.prog, u_w, u_vrow, h->tab.V, ks, 0, U, s);
+    h->launches += launch_penalty(h->prm, h->tab.prog, u_w, u_vrow, h->tab.V, h->tab.rs, 0, U, s);
+  }
+  if (h->profile) {
+    tm_upd.~StageTimer(); tm_upd.e = nullptr;
+    h->prof_steps++;
   }
   DFB_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+// fold the oldest outstanding snapshot of the pipelined path into *acc
+int collect_one(dfb_engine* h, DevProgress* acc) {
+  const int r = (int)(h->collected % dfb_engine::kRing);
+  DFB_CUDA(h, cudaEventSynchronize(h->ring_done[r]));
+  add_prog(*acc, h->h_ring[r]);
+  h->collected++;
   return 0;
 }
 
@@ -309,6 +422,11 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     else if (k == "V_capacity") { if (!need_int(0, 1LL << 30)) { delete h; return DFB_ERR_PARAM; } v_capacity = x; }
     else if (k == "compute_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->compute_auc = (int)x; }
     else if (k == "force_generic") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->force_generic = (int)x; }
+    else if (k == "scatter") {
+      if (v == "sorted") h->scatter_sorted = 1;
+      else if (v == "atomic") h->scatter_sorted = 0;
+      else return bad("scatter must be 'sorted' or 'atomic'");
+    }
     else h->unknown.push_back(std::make_pair(k, v));
   }
   if (p.V_dim < 0) return bad("Required parameter V_dim of int is not presented");   // sgd_param.h:104
@@ -337,10 +455,11 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   t.ks = (p.V_dim + 3) / 4 * 4;
   t.vcap = (uint64_t)v_capacity;
   if ((e = cudaMalloc(&t.tab, t.cap * sizeof(Entry))) != cudaSuccess) return cfail("cudaMalloc(table)");
+  t.rs = 2 * t.ks;
   if (t.vcap && t.ks) {
-    size_t vb = (size_t)t.vcap * t.ks * sizeof(float);
-    if ((e = cudaMalloc(&t.V, vb)) != cudaSuccess) return cfail("cudaMalloc(V)");
-    if ((e = cudaMalloc(&t.Vcg, vb)) != cudaSuccess) return cfail("cudaMalloc(Vcg)");
+    size_t vb = (size_t)t.vcap * t.rs * sizeof(float);
+    if ((e = cudaMalloc(&t.V, vb)) != cudaSuccess) return cfail("cudaMalloc(V rows)");
+    t.Vcg = t.V + t.ks;
   }
   if ((e = cudaMalloc(&t.state, sizeof(TableState))) != cudaSuccess) return cfail("cudaMalloc(state)");
   if ((e = cudaMalloc(&t.prog, 2 * sizeof(DevProgress))) != cudaSuccess) return cfail("cudaMalloc(prog)");
@@ -348,6 +467,11 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   if ((e = cudaHostAlloc(&h->h_prog, sizeof(DevProgress), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   if ((e = cudaHostAlloc(&h->h_nvals, sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   memset(h->h_prog, 0, sizeof(DevProgress));
+  if ((e = cudaHostAlloc(&h->h_ring, dfb_engine::kRing * sizeof(DevProgress), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
+  memset(h->h_ring, 0, dfb_engine::kRing * sizeof(DevProgress));
+  memset(&h->backlog, 0, sizeof(DevProgress));
+  for (auto& ev : h->ring_done)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
   h->launches += launch_table_init(t, p.seed, h->stream);
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cfail("table init");
   *out = h;
@@ -358,7 +482,8 @@ int dfb_destroy(dfb_handle h) {
   if (!h) return DFB_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
+  DevBuf* bufs[] = {&h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
+                    &h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
                     &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
                     &h->a_val, &h->a_lab, &h->a_w, &h->a_wpos, &h->a_vpos, &h->a_pred, &h->a_grad, &h->scal,
                     &h->hasv, &h->rV, &h->rcg, &h->nvals};
@@ -371,11 +496,13 @@ int dfb_destroy(dfb_handle h) {
   }
   if (h->tab.tab) cudaFree(h->tab.tab);
   if (h->tab.V) cudaFree(h->tab.V);
-  if (h->tab.Vcg) cudaFree(h->tab.Vcg);
   if (h->tab.state) cudaFree(h->tab.state);
   if (h->tab.prog) cudaFree(h->tab.prog);
   if (h->h_prog) cudaFreeHost(h->h_prog);
   if (h->h_nvals) cudaFreeHost(h->h_nvals);
+  if (h->h_ring) cudaFreeHost(h->h_ring);
+  for (auto& ev : h->ring_done) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->pev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -651,12 +778,13 @@ int dfb_auc(dfb_handle h, const float* label, const float* pred, size_t n, float
 // ------------------------------------------------------------------------------------------
 // (B) fused step
 // ------------------------------------------------------------------------------------------
-int dfb_train_step_dev(dfb_handle h, size_t nrows, const uint64_t* d_offset, const uint32_t* d_index,
+int dfb_train_step_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
                        const float* d_value_or_null, const float* d_label, const uint64_t* d_keys, size_t nkeys,
                        const float* d_cnt_or_null, int is_train) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
-  return step_dev(h, nrows, d_offset, d_index, d_value_or_null, d_label, d_keys, nkeys, d_cnt_or_null, is_train);
+  return step_dev(h, nrows, nnz, d_offset, d_index, d_value_or_null, d_label, d_keys, nkeys, d_cnt_or_null,
+                  is_train);
 }
 
 int dfb_sync(dfb_handle h) {
@@ -671,7 +799,15 @@ int dfb_read_progress(dfb_handle h, dfb_progress* out) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
   DFB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
-  return fetch_progress(h, out);
+  DevProgress acc = h->backlog;
+  memset(&h->backlog, 0, sizeof(DevProgress));
+  while (h->collected < h->submitted) DFB_TRY(collect_one(h, &acc));
+  int rc = fetch_progress(h, nullptr);    // what is still on the device (dfb_train_step_dev steps)
+  add_prog(acc, *h->h_prog);
+  if (out) to_public(acc, out);
+  if (rc != 0) return rc;
+  *h->h_prog = acc;
+  return check_dev_err(h);
 }
 
 int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index,
@@ -696,12 +832,57 @@ int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, con
   if (cnt) DFB_TRY(h2d(h, in.cnt, cnt, nkeys * sizeof(float), cs));
   DFB_CUDA(h, cudaEventRecord(in.copied, cs));
   DFB_CUDA(h, cudaStreamWaitEvent(h->stream, in.copied, 0));
-  int rc = step_dev(h, nrows, in.off.as<uint64_t>(), in.idx.as<uint32_t>(), value ? in.val.as<float>() : nullptr,
+  int rc = step_dev(h, nrows, nnz, in.off.as<uint64_t>(), in.idx.as<uint32_t>(), value ? in.val.as<float>() : nullptr,
                     in.lab.as<float>(), in.keys.as<uint64_t>(), nkeys, cnt ? in.cnt.as<float>() : nullptr,
                     is_train);
   DFB_CUDA(h, cudaEventRecord(in.consumed, h->stream));
   h->seq++;
-  return rc;
+  if (rc != 0) return rc;
+  // per-step snapshot of the Progress block: D2H into the pinned ring, then clear
+  if (h->submitted - h->collected == (uint64_t)dfb_engine::kRing) DFB_TRY(collect_one(h, &h->backlog));
+  const int r = (int)(h->submitted % dfb_engine::kRing);
+  DFB_CUDA(h, cudaMemcpyAsync(&h->h_ring[r], h->tab.prog, sizeof(DevProgress), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(h, cudaMemsetAsync(h->tab.prog, 0, sizeof(DevProgress), h->stream));
+  DFB_CUDA(h, cudaEventRecord(h->ring_done[r], h->stream));
+  h->submitted++;
+  return DFB_OK;
+}
+
+int dfb_wait_step(dfb_handle h, dfb_progress* out) {
+  if (!h) return DFB_ERR_INVALID;
+  if (h->submitted == h->collected) return h->fail(DFB_ERR_INVALID, "no outstanding step");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DevProgress one;
+  memset(&one, 0, sizeof(one));
+  DFB_TRY(collect_one(h, &one));
+  if (out) to_public(one, out);
+  *h->h_prog = one;
+  return check_dev_err(h);
+}
+
+int dfb_profile(dfb_handle h, int enable) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  if (enable && h->pev.empty()) {
+    h->pev.assign((size_t)dfb_engine::kProfRing * dfb_engine::kStages * 2, nullptr);
+    h->pev_used.assign((size_t)dfb_engine::kProfRing * dfb_engine::kStages, 0);
+    for (auto& ev : h->pev) DFB_CUDA(h, cudaEventCreate(&ev));
+  }
+  if (!enable && h->profile) DFB_TRY(prof_drain(h));
+  h->profile = enable ? 1 : 0;
+  return DFB_OK;
+}
+
+int dfb_profile_read(dfb_handle h, double* stage_ms, uint64_t* stage_count) {
+  if (!h || !stage_ms || !stage_count) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DFB_TRY(prof_drain(h));
+  for (int i = 0; i < dfb_engine::kStages; ++i) {
+    stage_ms[i] = h->stage_ms[i]; stage_count[i] = h->stage_n[i];
+    h->stage_ms[i] = 0; h->stage_n[i] = 0;
+  }
+  h->prof_steps = 0;
+  return DFB_OK;
 }
 
 int dfb_train_step(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index, const float* value,
@@ -711,7 +892,7 @@ int dfb_train_step(dfb_handle h, size_t nrows, const uint64_t* offset, const uin
   DFB_TRY(dfb_train_step_async(h, nrows, offset, index, value, label, keys, nkeys, cnt, is_train));
   if (pred_out && nrows)
     DFB_CUDA(h, cudaMemcpyAsync(pred_out, h->pred.p, nrows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  return fetch_progress(h, out);
+  return dfb_read_progress(h, out);
 }
 
 int dfb_read_entries(dfb_handle h, const uint64_t* keys, size_t n, float* scal_out, int* has_V_out, float* V_out,
@@ -796,13 +977,14 @@ int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w
   return DFB_OK;
 }
 
-int dfb_dev_fm_step(dfb_handle h, size_t nrows, const uint64_t* d_offset, const uint32_t* d_index,
+int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
                     const float* d_value, const float* d_label, size_t nkeys, const float* d_w, const int* d_hasv,
                     const float* d_V, int is_train, float* d_gw_out, float* d_gxxp_out, float* d_gV_out) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const int ks = h->tab.ks, k = h->prm.V_dim;
+  const bool sorted = is_train && h->scatter_sorted && !h->force_generic && fm_fast_supported(k) && ks == k;
   DFB_TRY(h->ensure(h->pred, nrows * sizeof(float)));
   FmView v;
   memset(&v, 0, sizeof(v));
@@ -811,19 +993,37 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, const uint64_t* d_offset, const 
   if (is_train) {
     if (!d_gw_out || (k > 0 && !d_gV_out) || (k > 0 && d_value && !d_gxxp_out))
       return h->fail(DFB_ERR_INVALID, "gradient outputs are NULL");
-    DFB_CUDA(h, cudaMemsetAsync(d_gw_out, 0, nkeys * sizeof(float), s));
-    if (k > 0) DFB_CUDA(h, cudaMemsetAsync(d_gV_out, 0, nkeys * (size_t)ks * sizeof(float), s));
-    if (k > 0 && d_gxxp_out) DFB_CUDA(h, cudaMemsetAsync(d_gxxp_out, 0, nkeys * sizeof(float), s));
-    v.gwbase = d_gw_out; v.gvbase = d_gV_out; v.gvstride = ks;
-    v.gxxp = (k > 0 && d_value) ? d_gxxp_out : nullptr;
+    if (sorted) {
+      DFB_TRY(ensure_sorted_ws(h, nrows, nnz, nkeys, d_value != nullptr));
+    } else {
+      DFB_CUDA(h, cudaMemsetAsync(d_gw_out, 0, nkeys * sizeof(float), s));
+      if (k > 0) DFB_CUDA(h, cudaMemsetAsync(d_gV_out, 0, nkeys * (size_t)ks * sizeof(float), s));
+      if (k > 0 && d_gxxp_out) DFB_CUDA(h, cudaMemsetAsync(d_gxxp_out, 0, nkeys * sizeof(float), s));
+      v.gwbase = d_gw_out; v.gvbase = d_gV_out; v.gvstride = ks;
+      v.gxxp = (k > 0 && d_value) ? d_gxxp_out : nullptr;
+    }
   }
   FmBatch b;
   memset(&b, 0, sizeof(b));
   b.nrows = nrows; b.offset = d_offset; b.index = d_index; b.value = d_value; b.label = d_label;
   b.pred_io = h->pred.as<float>(); b.V_dim = k; b.train = is_train; b.prog = h->tab.prog;
+  if (sorted) {
+    b.emit = 1; b.p_out = h->p_row.as<float>(); b.pxv_out = h->pxv.as<float>();
+    b.occ_row = h->occ.as<uint32_t>(); b.occ_rowx = h->occ.as<unsigned long long>();
+  }
   if (nrows) {
     int nl = launch_fm(b, v, h->force_generic, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
+    h->launches += nl;
+  }
+  if (sorted) {
+    h->launches += launch_csc_build(d_index, h->occ.p, d_value != nullptr, nnz, nkeys, h->lidx_sorted.as<uint32_t>(),
+                                    h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
+                                    h->cub.bytes, s);
+    int nl = launch_bwd_dense(k, ks, d_hasv, nkeys, h->col_start.as<int>(), h->col_end.as<int>(), h->occ_sorted.p,
+                              d_value != nullptr, h->p_row.as<float>(), h->pxv.as<float>(), d_gw_out,
+                              d_value ? d_gxxp_out : nullptr, d_gV_out, s);
+    if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
     h->launches += nl;
   }
   if (h->compute_auc && nrows) {

@@ -77,8 +77,12 @@ __device__ __forceinline__ void block_add_loss(float loss_acc, size_t nrows, Dev
 // ---------------------------------------------------------------------------------------
 // fast path: K in {8,16,32,64,128}, 16-byte aligned rows
 // ---------------------------------------------------------------------------------------
-template <int K, bool TRAIN, bool HAS_VAL>
+// MODE 0: predict only.  MODE 1: training with fp32 red.global scatter into dense gradient rows.
+// MODE 2: training, "emit": writes p_i, p_i*XV_i and the (row[,x]) payload of every nnz so that
+//         the gradient can be reduced per key without atomics (kernels_table.cu: k_bwd_update).
+template <int K, int MODE, bool HAS_VAL>
 __global__ void __launch_bounds__(256) k_fm_fast(FmBatch b, FmView v) {
+  constexpr bool TRAIN = MODE == 1;
   constexpr int LPR = K / 4;                 // lanes per V row, one float4 each
   constexpr int G = 32 / LPR;                // V rows fetched by one warp-wide load
   constexpr int UNR = (32 / G) < 8 ? (32 / G) : 8;   // independent loads in flight per lane
@@ -106,6 +110,10 @@ __global__ void __launch_bounds__(256) k_fm_fast(FmBatch b, FmView v) {
         w = wp >= 0 ? __ldg(v.wbase + wp) : 0.f;
         vr = __ldg(v.v_pos + u);
         if (v.dense && vr >= 0) vr = (int)u;
+        if (MODE == 2) {
+          if (HAS_VAL) b.occ_rowx[j] = ((unsigned long long)row << 32) | (unsigned long long)__float_as_uint(x);
+          else b.occ_row[j] = (uint32_t)row;
+        }
       }
       wsum = fmaf(x, w, wsum);
       const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
@@ -151,6 +159,14 @@ __global__ void __launch_bounds__(256) k_fm_fast(FmBatch b, FmView v) {
     if (lane == 0) {
       if (b.pred_io) b.pred_io[row] = pred;
       if (b.label) loss_acc += row_logloss(label, pred);
+    }
+    if (MODE == 2) {
+      const float p = row_p(label, pred);
+      if (lane == 0) b.p_out[row] = p;
+      // XV_ *= p (fm_loss.h:191-195), one coalesced 4K-byte row
+      if (grp == 0)
+        *reinterpret_cast<float4*>(b.pxv_out + row * (size_t)K + sub * 4) =
+            make_float4(p * xv.x, p * xv.y, p * xv.z, p * xv.w);
     }
 
     if (TRAIN) {
@@ -312,25 +328,31 @@ int launch_fast_k(const FmBatch& b, const FmView& v, cudaStream_t s) {
   size_t need = (b.nrows + 7) / 8;
   int grid = (int)(need < (size_t)(148 * 8) ? (need ? need : 1) : (size_t)(148 * 8));
   const bool hv = b.value != nullptr;
-  if (b.train) {
-    if (hv) k_fm_fast<K, true, true><<<grid, threads, 0, s>>>(b, v);
-    else    k_fm_fast<K, true, false><<<grid, threads, 0, s>>>(b, v);
+  if (b.train && b.emit) {
+    if (hv) k_fm_fast<K, 2, true><<<grid, threads, 0, s>>>(b, v);
+    else    k_fm_fast<K, 2, false><<<grid, threads, 0, s>>>(b, v);
+  } else if (b.train) {
+    if (hv) k_fm_fast<K, 1, true><<<grid, threads, 0, s>>>(b, v);
+    else    k_fm_fast<K, 1, false><<<grid, threads, 0, s>>>(b, v);
   } else {
-    if (hv) k_fm_fast<K, false, true><<<grid, threads, 0, s>>>(b, v);
-    else    k_fm_fast<K, false, false><<<grid, threads, 0, s>>>(b, v);
+    if (hv) k_fm_fast<K, 0, true><<<grid, threads, 0, s>>>(b, v);
+    else    k_fm_fast<K, 0, false><<<grid, threads, 0, s>>>(b, v);
   }
   return 1;
 }
 
 }  // namespace
 
+bool fm_fast_supported(int k) { return k == 8 || k == 16 || k == 32 || k == 64 || k == 128; }
+
 int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t s) {
   const int k = b.V_dim;
   bool fast = !force_generic && (k == 8 || k == 16 || k == 32 || k == 64 || k == 128) &&
               v.v_pos != nullptr && aligned16(v.vbase) && (v.vstride % 4 == 0);
-  if (fast && b.train) {
+  if (fast && b.train && !b.emit) {
     fast = aligned16(v.gvbase) && (v.gvstride % 4 == 0) && (b.value == nullptr || v.gxxp != nullptr);
   }
+  if (b.train && b.emit && !fast) return -1;   // the emit mode exists only on the fast path
   if (fast) {
     switch (k) {
       case 8: return launch_fast_k<8>(b, v, s);

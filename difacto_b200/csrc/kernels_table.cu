@@ -141,34 +141,42 @@ __device__ __forceinline__ int rand_r_dev(unsigned* seed) {
   return (int)result;
 }
 
-// InitV (sgd_updater.cc:140-147) for the flagged keys; pos = exclusive scan of flags
+// InitV (sgd_updater.cc:140-147) for the flagged keys; pos = exclusive scan of flags.
+// A warp scans 32 flags at a time (almost always all zero) and cooperates on each set one.
 __global__ void k_initv(Table t, Params p, const int* __restrict__ slot, size_t n,
                         const int* __restrict__ flags, const int* __restrict__ pos) {
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  const unsigned long long vbase = t.state->n_vrows;
-  const unsigned seed0 = t.state->seed;
   const int k = p.V_dim;
-  for (size_t i = warp0; i < n; i += nwarps) {
-    if (!flags[i]) continue;
-    const unsigned long long r = vbase + (unsigned long long)pos[i];
-    if (r >= t.vcap) { if (lane == 0) raise(t.prog, DFB_ERR_CAPACITY); continue; }
-    float* Vr = t.V + r * t.ks;
-    float* Cr = t.Vcg + r * t.ks;
-    for (int l = lane; l < t.ks; l += 32) {
-      float val = 0.f;
-      if (l < k) {
-        unsigned sd = lcg_jump(seed0, 3ULL * ((unsigned long long)pos[i] * k + l));
-        const int rr = rand_r_dev(&sd);
-        // (rand_r / (real_t)RAND_MAX - 0.5) * V_init_scale: float division, then double
-        const float u01 = __fdiv_rn((float)rr, 2147483648.0f);
-        val = __double2float_rn(__dmul_rn(__dsub_rn((double)u01, 0.5), (double)p.V_init_scale));
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t mine = base + lane;
+    unsigned m = __ballot_sync(kFull, mine < n && flags[mine] != 0);
+    if (m == 0) continue;
+    const unsigned long long vbase = t.state->n_vrows;
+    const unsigned seed0 = t.state->seed;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const size_t i = base + b;
+      const unsigned long long r = vbase + (unsigned long long)pos[i];
+      if (r >= t.vcap) { if (lane == 0) raise(t.prog, DFB_ERR_CAPACITY); continue; }
+      float* Vr = t.V + r * t.rs;
+      float* Cr = t.Vcg + r * t.rs;
+      for (int l = lane; l < t.ks; l += 32) {
+        float val = 0.f;
+        if (l < k) {
+          unsigned sd = lcg_jump(seed0, 3ULL * ((unsigned long long)pos[i] * k + l));
+          const int rr = rand_r_dev(&sd);
+          // (rand_r / (real_t)RAND_MAX - 0.5) * V_init_scale: float division, then double
+          const float u01 = __fdiv_rn((float)rr, 2147483648.0f);
+          val = __double2float_rn(__dmul_rn(__dsub_rn((double)u01, 0.5), (double)p.V_init_scale));
+        }
+        Vr[l] = val;
+        Cr[l] = 0.f;
       }
-      Vr[l] = val;
-      Cr[l] = 0.f;
+      if (lane == 0) t.tab[slot[i]].vrow = (int)r;
     }
-    if (lane == 0) t.tab[slot[i]].vrow = (int)r;
   }
 }
 
@@ -245,8 +253,8 @@ __global__ void __launch_bounds__(256) k_update_fast(Table t, Params p, const in
     }
     if (vr >= 0) {
       const float xxp = gxxp ? gxxp[i] : g_w;
-      float* Vr = t.V + (size_t)vr * t.ks + sub * 4;
-      float* Cr = t.Vcg + (size_t)vr * t.ks + sub * 4;
+      float* Vr = t.V + (size_t)vr * t.rs + sub * 4;
+      float* Cr = t.Vcg + (size_t)vr * t.rs + sub * 4;
       float4 v = *reinterpret_cast<const float4*>(Vr);
       float4 c = *reinterpret_cast<const float4*>(Cr);
       const float4 g = __ldg(reinterpret_cast<const float4*>(gV + i * (size_t)t.ks + sub * 4));
@@ -295,8 +303,8 @@ __global__ void __launch_bounds__(256) k_update_dense_generic(Table t, Params p,
     }
     if (vr >= 0) {
       const float xxp = gxxp ? gxxp[i] : g_w;
-      float* Vr = t.V + (size_t)vr * t.ks;
-      float* Cr = t.Vcg + (size_t)vr * t.ks;
+      float* Vr = t.V + (size_t)vr * t.rs;
+      float* Cr = t.Vcg + (size_t)vr * t.rs;
       const float* g = gV + i * (size_t)t.ks;
       for (int l = lane; l < k; l += 32) {
         float v = Vr[l], c = Cr[l];
@@ -338,8 +346,8 @@ __global__ void __launch_bounds__(256) k_update_ragged(Table t, Params p, const 
     if (len > 1) {
       // CHECK_EQ(lens[i], V_dim+1); CHECK(e.V != nullptr)  (sgd_updater.cc:92-93)
       if (len != k + 1 || vr < 0) { if (lane == 0) raise(t.prog, DFB_ERR_INVALID); continue; }
-      float* Vr = t.V + (size_t)vr * t.ks;
-      float* Cr = t.Vcg + (size_t)vr * t.ks;
+      float* Vr = t.V + (size_t)vr * t.rs;
+      float* Cr = t.Vcg + (size_t)vr * t.rs;
       const float* g = grads + off + 1;
       for (int l = lane; l < k; l += 32) {
         float v = Vr[l], c = Cr[l];
@@ -405,7 +413,7 @@ __global__ void k_pack_ragged(Table t, Params p, const int* __restrict__ slot, s
     const size_t off = (size_t)pos[i];
     if (lane == 0) vals[off] = s >= 0 ? t.tab[s].w : 0.f;
     if (lens[i] > 1) {
-      const float* Vr = t.V + (size_t)t.tab[s].vrow * t.ks;
+      const float* Vr = t.V + (size_t)t.tab[s].vrow * t.rs;
       for (int l = lane; l < k; l += 32) vals[off + 1 + l] = Vr[l];
     }
     if (i == n - 1 && lane == 0) *nvals_out = (unsigned long long)pos[i] + (unsigned long long)lens[i];
@@ -425,7 +433,7 @@ __global__ void k_gather_rows(Table t, const int* __restrict__ slot, size_t n, f
       hasv_out[i] = vr >= 0 ? 1 : -1;
     }
     if (vr >= 0 && V_out) {
-      const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vr * t.ks);
+      const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vr * t.rs);
       float4* dst = reinterpret_cast<float4*>(V_out + i * (size_t)t.ks);
       for (int l = lane; l < t.ks / 4; l += 32) dst[l] = src[l];
     }
@@ -447,8 +455,8 @@ __global__ void k_read_entries(Table t, const int* __restrict__ slot, size_t n, 
   hasv[i] = e.vrow >= 0 ? 1 : 0;
   if (e.vrow >= 0) {
     for (int l = 0; l < k; ++l) {
-      if (V) V[i * (size_t)k + l] = t.V[(size_t)e.vrow * t.ks + l];
-      if (cg) cg[i * (size_t)k + l] = t.Vcg[(size_t)e.vrow * t.ks + l];
+      if (V) V[i * (size_t)k + l] = t.V[(size_t)e.vrow * t.rs + l];
+      if (cg) cg[i * (size_t)k + l] = t.Vcg[(size_t)e.vrow * t.rs + l];
     }
   }
 }
@@ -512,6 +520,125 @@ __global__ void __launch_bounds__(1024) k_auc_area(const float* __restrict__ sor
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// sorted (atomic-free) gradient reduction
+// ---------------------------------------------------------------------------------------
+// boundaries of the runs of equal key ids in the sorted id list
+__global__ void k_col_bounds(const uint32_t* __restrict__ sorted, size_t n, int* __restrict__ col_start,
+                             int* __restrict__ col_end) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t cur = sorted[j];
+  if (j == 0) col_start[cur] = 0;
+  else {
+    const uint32_t prev = sorted[j - 1];
+    if (prev != cur) { col_start[cur] = (int)j; col_end[prev] = (int)j; }
+  }
+  if (j == n - 1) col_end[cur] = (int)n;
+}
+
+template <bool HAS_VAL>
+__device__ __forceinline__ void load_occ(const void* occ, int o, uint32_t& row, float& x) {
+  if (HAS_VAL) {
+    const unsigned long long rx = __ldg(reinterpret_cast<const unsigned long long*>(occ) + o);
+    row = (uint32_t)(rx >> 32);
+    x = __uint_as_float((uint32_t)rx);
+  } else {
+    row = __ldg(reinterpret_cast<const uint32_t*>(occ) + o);
+    x = 1.f;
+  }
+}
+
+// Per unique key: grad_w = sum x p_i, XXp = sum x^2 p_i, grad_V = sum x (p XV)_i - V XXp
+// (fm_loss.h:164-198, summed in row order like SpMM::TransTimes), immediately consumed by
+// FTRL (w) and AdaGrad (V): the gradient never exists in HBM.  APPLY=false writes the dense
+// gradient rows instead (worker side of the sharded store).
+template <int K, bool HAS_VAL, bool APPLY>
+__global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int* __restrict__ slot,
+                                                    const int* __restrict__ pull_vrow, size_t n,
+                                                    const int* __restrict__ col_start,
+                                                    const int* __restrict__ col_end,
+                                                    const void* __restrict__ occ,
+                                                    const float* __restrict__ p_row,
+                                                    const float* __restrict__ pxv, int* __restrict__ flags,
+                                                    int acc_pen, float* __restrict__ gw_out,
+                                                    float* __restrict__ gxxp_out, float* __restrict__ gV_out) {
+  constexpr int LPR = K / 4;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  float pen = 0.f;
+  for (size_t base = warp0 * G; base < n; base += nwarps * G) {
+    const size_t i = base + grp;
+    if (i >= n) continue;
+    int s = 0;
+    int vr = pull_vrow[i];
+    Entry* e = nullptr;
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), v = sc, c = sc;
+    float* Vr = nullptr;
+    if (APPLY) {
+      s = slot[i];
+      if (s < 0) { if (sub == 0) flags[i] = 0; continue; }
+      e = &t.tab[s];
+      // the table loads do not depend on the occurrence list: issue them first
+      if (sub == 0) sc = *reinterpret_cast<const float4*>(&e->fea_cnt);
+      if (vr >= 0) {
+        Vr = t.V + (size_t)vr * t.rs + sub * 4;
+        v = *reinterpret_cast<const float4*>(Vr);
+        c = *reinterpret_cast<const float4*>(Vr + t.ks);
+      }
+    }
+    const int o0 = col_start[i], o1 = col_end[i];
+    float gw = 0.f, xxp = 0.f;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int o = o0; o < o1; ++o) {
+      uint32_t row; float x;
+      load_occ<HAS_VAL>(occ, o, row, x);
+      const float pr = __ldg(p_row + row);
+      gw = __fadd_rn(gw, __fmul_rn(pr, x));                        // spmv.h:162-164
+      if (HAS_VAL) xxp = __fadd_rn(xxp, __fmul_rn(pr, __fmul_rn(x, x)));
+      if (vr >= 0) {
+        const float4 tt = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)row * K + sub * 4));
+        g.x = __fadd_rn(g.x, __fmul_rn(tt.x, x)); g.y = __fadd_rn(g.y, __fmul_rn(tt.y, x));   // spmm.h:152-154
+        g.z = __fadd_rn(g.z, __fmul_rn(tt.z, x)); g.w = __fadd_rn(g.w, __fmul_rn(tt.w, x));
+      }
+    }
+    if (!HAS_VAL) xxp = gw;
+    if (APPLY) {
+      if (sub == 0) {
+        if (acc_pen) pen += pen_w(p, sc.y);
+        const bool became_nz = ftrl_step(p, gw, sc.y, sc.z, sc.w);
+        *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
+        flags[i] = (became_nz && p.V_dim > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
+      }
+      if (vr >= 0) {
+        if (acc_pen) pen += 0.5f * p.V_l2 * (v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+        adagrad_step(p, __fsub_rn(g.x, __fmul_rn(v.x, xxp)), v.x, c.x);
+        adagrad_step(p, __fsub_rn(g.y, __fmul_rn(v.y, xxp)), v.y, c.y);
+        adagrad_step(p, __fsub_rn(g.z, __fmul_rn(v.z, xxp)), v.z, c.z);
+        adagrad_step(p, __fsub_rn(g.w, __fmul_rn(v.w, xxp)), v.w, c.w);
+        *reinterpret_cast<float4*>(Vr) = v;
+        *reinterpret_cast<float4*>(Vr + t.ks) = c;
+      }
+    } else {
+      if (sub == 0) { gw_out[i] = gw; if (gxxp_out) gxxp_out[i] = xxp; }
+      if (vr >= 0) *reinterpret_cast<float4*>(gV_out + i * (size_t)K + sub * 4) = g;
+    }
+  }
+  if (APPLY && acc_pen) {
+    pen = warp_sum(pen);
+    if (lane == 0 && pen != 0.f) atomicAdd(&t.prog->penalty, (double)pen);
+  }
+}
+
+inline int bits_for(size_t n) {
+  int b = 1;
+  while (b < 32 && ((size_t)1 << b) < n) ++b;
+  return b;
+}
+
 inline int grid_for(size_t n, int threads, int cap) {
   size_t g = (n + threads - 1) / threads;
   if (g == 0) g = 1;
@@ -557,7 +684,7 @@ int launch_initv(Table& t, const Params& p, const int* slot, size_t n, int* flag
                  size_t cub_bytes, cudaStream_t s) {
   if (n == 0 || p.V_dim == 0) return 0;
   cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, (int)n, s);
-  k_initv<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, p, slot, n, flags, pos);
+  k_initv<<<grid_warps((n + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, p, slot, n, flags, pos);
   k_initv_finalize<<<1, 32, 0, s>>>(t, p, n, flags, pos);
   return 4;  // the CUB scan is 2 kernels
 }
@@ -648,6 +775,90 @@ int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp, 
   cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, pred, key_tmp2, label, val_tmp2, (int)n, 0, 32, s);
   k_auc_area<<<1, 1024, 0, s>>>(val_tmp2, n, out_add);
   return 4;
+}
+
+
+size_t csc_tmp_bytes(size_t nnz, bool valued) {
+  size_t bytes = 0;
+  const int n = (int)(nnz ? nnz : 1);
+  if (valued)
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n);
+  else
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+  return bytes;
+}
+
+int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t nnz, size_t nkeys,
+                     uint32_t* lidx_sorted, void* occ_sorted, int* col_start, int* col_end, void* cub_tmp,
+                     size_t cub_bytes, cudaStream_t s) {
+  if (nkeys == 0) return 0;
+  cudaMemsetAsync(col_start, 0, nkeys * sizeof(int), s);
+  cudaMemsetAsync(col_end, 0, nkeys * sizeof(int), s);
+  if (nnz == 0) return 0;
+  const int eb = bits_for(nkeys);
+  if (valued)
+    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, lidx, lidx_sorted,
+                                    reinterpret_cast<const unsigned long long*>(occ),
+                                    reinterpret_cast<unsigned long long*>(occ_sorted), (int)nnz, 0, eb, s);
+  else
+    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, lidx, lidx_sorted,
+                                    reinterpret_cast<const uint32_t*>(occ),
+                                    reinterpret_cast<uint32_t*>(occ_sorted), (int)nnz, 0, eb, s);
+  k_col_bounds<<<(int)((nnz + 255) / 256), 256, 0, s>>>(lidx_sorted, nnz, col_start, col_end);
+  return 2 + (eb + 7) / 8;   // histogram + one onesweep pass per 8 key bits + bounds
+}
+
+int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,
+                      const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
+                      const float* p_row, const float* pxv, int* flags, int acc_pen, cudaStream_t s) {
+  if (n == 0) return 0;
+#define DFB_BU(K)                                                                                          \
+  do {                                                                                                     \
+    const int grid = grid_warps((n + (32 / (K / 4)) - 1) / (32 / (K / 4)), 8, 148 * 8);                      \
+    if (valued) k_bwd_update<K, true, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end, \
+                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr);                      \
+    else k_bwd_update<K, false, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end,     \
+                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr);                      \
+  } while (0)
+  switch (p.V_dim) {
+    case 8: DFB_BU(8); return 1;
+    case 16: DFB_BU(16); return 1;
+    case 32: DFB_BU(32); return 1;
+    case 64: DFB_BU(64); return 1;
+    case 128: DFB_BU(128); return 1;
+  }
+#undef DFB_BU
+  return -1;
+}
+
+int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* col_start, const int* col_end,
+                     const void* occ_sorted, bool valued, const float* p_row, const float* pxv, float* gw_out,
+                     float* gxxp_out, float* gV_out, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (ks != V_dim) return -1;
+  Table t;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.V_dim = V_dim;
+#define DFB_BD(K)                                                                                          \
+  do {                                                                                                     \
+    const int grid = grid_warps((n + (32 / (K / 4)) - 1) / (32 / (K / 4)), 8, 148 * 8);                      \
+    if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, nullptr, hasv, n, col_start, col_end, \
+                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, gxxp_out, gV_out);                           \
+    else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, nullptr, hasv, n, col_start, col_end,      \
+                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, gxxp_out, gV_out);                           \
+  } while (0)
+  switch (V_dim) {
+    case 8: DFB_BD(8); return 1;
+    case 16: DFB_BD(16); return 1;
+    case 32: DFB_BD(32); return 1;
+    case 64: DFB_BD(64); return 1;
+    case 128: DFB_BD(128); return 1;
+  }
+#undef DFB_BD
+  return -1;
 }
 
 int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* hasv, float* V, float* cg,

@@ -67,10 +67,12 @@ typedef struct {
  *   device (0)            CUDA device ordinal
  *   table_capacity (1<<20) max number of distinct keys this shard can hold
  *   V_capacity (=table_capacity) max number of keys with an allocated V row
- *   max_batch_nnz / max_batch_rows / max_batch_keys   workspace sizing hints (grow on demand)
  *   compute_auc (1)       evaluate AUC on device each step (sgd_learner.cc:150-153)
- *   deterministic (0)     1 = gradient scatter through a sorted segmented reduction
- *                         (bit-reproducible); 0 = fp32 red.global atomics
+ *   scatter (sorted)      sorted = gradient reduced per key through a stable radix-sorted CSC view of
+ *                         the batch, fused with the FTRL/AdaGrad step (no atomics, bit-reproducible,
+ *                         row order per key like SpMM::TransTimes); atomic = fp32 red.global scatter
+ *                         into dense gradient rows followed by a separate update kernel
+ *   force_generic (0)     1 = use the any-V_dim kernels even where a specialised one exists (tests)
  * Keys that are neither are returned through dfb_unknown_kwarg, mirroring the
  * "return the unconsumed kwargs" convention (updater.h:34, main.cc:25-31).
  * ------------------------------------------------------------------------------- */
@@ -152,7 +154,7 @@ int dfb_train_step(dfb_handle h, size_t nrows, const uint64_t* offset, const uin
 /* same, but every array is already resident in device memory on the handle's device and
  * the call only enqueues work on the handle's stream (no host synchronisation);
  * dfb_sync() / dfb_read_progress() collect the result. */
-int dfb_train_step_dev(dfb_handle h, size_t nrows, const uint64_t* d_offset,
+int dfb_train_step_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset,
                        const uint32_t* d_index, const float* d_value_or_null,
                        const float* d_label, const uint64_t* d_keys, size_t nkeys,
                        const float* d_cnt_or_null, int is_train);
@@ -168,6 +170,17 @@ int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset,
                          const uint32_t* index, const float* value_or_null, const float* label,
                          const uint64_t* keys, size_t nkeys, const float* cnt_or_null,
                          int is_train);
+
+/* blocks until the OLDEST not yet collected dfb_train_step_async step has finished and
+ * returns that step's Progress (each async step snapshots its Progress into a pinned ring,
+ * so collecting step t does not drain step t+1 from the pipeline). */
+int dfb_wait_step(dfb_handle h, dfb_progress* out);
+
+/* per-stage device timing with CUDA events on the handle's stream (bench.py's roofline):
+ * stage 0 = key lookup + pull, 1 = FM forward/backward kernel, 2 = AUC, 3 = FTRL/AdaGrad update.
+ * dfb_profile_read returns the accumulated milliseconds and launch counts and resets them. */
+int dfb_profile(dfb_handle h, int enable);
+int dfb_profile_read(dfb_handle h, double* stage_ms4, uint64_t* stage_count4);
 
 /* ---------------------------------------------------------------------------------
  * model inspection (tests, checkpointing): read entries of the table.
@@ -199,7 +212,7 @@ int dfb_row_stride(dfb_handle h);  /* ks: V_dim rounded up to a multiple of 4 fl
 int dfb_dev_feacnt(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_cnt);
 int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w_out,
                       int* d_hasv_out, float* d_V_out);
-int dfb_dev_fm_step(dfb_handle h, size_t nrows, const uint64_t* d_offset,
+int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset,
                     const uint32_t* d_index, const float* d_value_or_null, const float* d_label,
                     size_t nkeys, const float* d_w, const int* d_hasv, const float* d_V,
                     int is_train, float* d_gw_out, float* d_gxxp_out, float* d_gV_out);

@@ -184,9 +184,9 @@ def test_param_errors_mirror_dmlc():
 # ----------------------------------------------------------------------------------------
 # (B) fused step vs the oracle's IterateData, whole trajectories
 # ----------------------------------------------------------------------------------------
-def run_both(kw, batches, epochs, force_generic=0, feacnt_epochs=1, val_every=0):
+def run_both(kw, batches, epochs, force_generic=0, feacnt_epochs=1, val_every=0, scatter="sorted"):
     M = O.Oracle(**kw)
-    E = engine(force_generic=force_generic, **kw)
+    E = engine(force_generic=force_generic, scatter=scatter, **kw)
     t = 0
     for ep in range(epochs):
         for (o, l, i, v) in batches:
@@ -262,13 +262,16 @@ def test_fused_synthetic_trace_vs_reference(refout, force_generic):
     assert_close(vals, refout["syn_final_vals"], what="final [w,V]", **STATE_TOL)
 
 
-@pytest.mark.parametrize("V_dim,valued,force_generic", [(0, True, 0), (5, True, 0), (8, False, 0), (16, True, 0),
-                                                        (32, False, 0), (64, True, 0), (64, False, 1), (128, False, 0)])
-def test_fused_trajectory_vs_oracle(V_dim, valued, force_generic):
+@pytest.mark.parametrize("V_dim,valued,force_generic,scatter",
+                         [(0, True, 0, "sorted"), (5, True, 0, "sorted"), (8, False, 0, "sorted"), (8, True, 0, "atomic"),
+                          (16, True, 0, "sorted"), (16, False, 0, "atomic"), (32, False, 0, "sorted"),
+                          (64, True, 0, "sorted"), (64, True, 0, "atomic"), (64, False, 1, "sorted"),
+                          (128, False, 0, "sorted"), (128, True, 0, "atomic")])
+def test_fused_trajectory_vs_oracle(V_dim, valued, force_generic, scatter):
     rng = np.random.default_rng(1000 + V_dim)
     kw = dict(V_dim=V_dim, l1=0.3, l2=0.01, lr=0.2, V_lr=0.05, V_threshold=4, V_l2=0.02, V_init_scale=0.2, seed=5)
     batches = [rand_batch(rng, 128, 30, 400, valued and j % 2 == 0) for j in range(5)]
-    M, E = run_both(kw, batches, epochs=4, force_generic=force_generic, val_every=4)
+    M, E = run_both(kw, batches, epochs=4, force_generic=force_generic, val_every=4, scatter=scatter)
     keys = np.unique(np.concatenate([O.reverse_bytes_np(b[2]) for b in batches]))
     ohasv = compare_state(M, E, keys)
     assert E.rng_state() == M.seed()
@@ -317,9 +320,27 @@ def test_validation_step_does_not_update():
     assert np.array_equal(p1, p2) and pr1.loss == pr2.loss     # forward is deterministic
 
 
+def test_sorted_scatter_is_bit_reproducible():
+    # the sorted reduction sums each key's contributions in row order: two runs are bit-identical,
+    # and hot keys (many occurrences) are reduced in the reference's order (spmm.h:140-156)
+    rng = np.random.default_rng(21)
+    kw = dict(V_dim=32, l1=0.01, lr=0.1, V_threshold=0, seed=9, scatter="sorted")
+    batches = [localized(rand_batch(rng, 512, 40, 60, j % 2 == 0)) for j in range(4)]   # 60 ids: heavy reuse
+    states = []
+    for rep in range(2):
+        E = engine(**kw)
+        for ep in range(3):
+            for b in batches:
+                E.train_step(b["offset"], b["lidx"], b["value"], b["label"], b["keys"], b["cnt"] if ep == 0 else None, True)
+        keys = np.unique(np.concatenate([b["keys"] for b in batches]))
+        states.append(E.read_entries(keys))
+    for a, b in zip(*states):
+        assert np.array_equal(a, b)
+
+
 def test_async_pipeline_equals_sync():
     rng = np.random.default_rng(12)
-    kw = dict(V_dim=32, l1=0.05, lr=0.1, V_threshold=1, seed=4, deterministic=0)
+    kw = dict(V_dim=32, l1=0.05, lr=0.1, V_threshold=1, seed=4)
     batches = [localized(rand_batch(rng, 200, 25, 800, False)) for _ in range(6)]
     A, S = engine(**kw), engine(**kw)
     for b in batches:
