@@ -289,7 +289,6 @@ def main_b200(args, rank, world, local_rank):
     for t in range(args.warmup):
         step_dev(t % nb)
     E.sync()
-    E.profile(True)
     launches0 = E.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -303,10 +302,17 @@ def main_b200(args, rank, world, local_rank):
     wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = E.launch_count() - launches0
-    stages = E.profile_read()
-    E.profile(False)
     prog = E.read_progress()
     value = args.steps * B / (ms * 1e-3)
+
+    # ---- the same steps again with per-stage CUDA events (kernel durations for the roofline) ----
+    E.profile(True)
+    for t in range(args.steps):
+        step_dev((args.warmup + t) % nb)
+    E.sync()
+    stages = E.profile_read()
+    E.profile(False)
+    E.read_progress()
 
     # ---- forward-only launches (validation batches): the pure gather+interaction kernel K1 ----
     E.profile(True)
@@ -354,21 +360,35 @@ def main_b200(args, rank, world, local_rank):
     peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     k = args.vdim
-    bytes_fwd = N * (4 * k + 8) + 16 * B                    # gather + interaction (K1)
-    bytes_bwd_scatter = N * 4 * (k + 1)                     # scatter-add of grad rows (no second gather here)
+    U = U_mean
+    # algorithmic bytes:
+    #  K1 gather+interaction: N(4k+8) + 16B
+    #  emit variant used in training adds the p*XV rows (4kB + 4B) and the per-nnz row payload (4N)
+    #  K2+K3 fused per-key reduce + FTRL/AdaGrad: per key read {entry 16, V|cg 8k, slot/vrow/col 16},
+    #     write {entry 16, V|cg 8k}; per nnz read {p*XV row 4k, p 4, payload 4}
+    bytes_fwd = N * (4 * k + 8) + 16 * B
+    bytes_emit = bytes_fwd + B * (4 * k + 4) + 4 * N
+    bytes_upd = U * (2 * (8 * k + 16) + 16) + N * (4 * k + 8)
+    upd = stages["update"]
+    upd_ms = upd["ms"] / max(upd["count"], 1)
     fm = stages["fm"]
     fm_ms = fm["ms"] / max(fm["count"], 1)
-    ach = (bytes_fwd + bytes_bwd_scatter) / (fm_ms * 1e-3) / 1e9 if fm_ms > 0 else 0.0
+    ach_upd = bytes_upd / (upd_ms * 1e-3) / 1e9 if upd_ms > 0 else 0.0
+    ach_fm = bytes_emit / (fm_ms * 1e-3) / 1e9 if fm_ms > 0 else 0.0
     fwd = stages_fwd["fm"]
     fwd_ms = fwd["ms"] / max(fwd["count"], 1)
     ach_fwd = bytes_fwd / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": f"k_fm_fast<{k},train> (fused gather+interaction+grad scatter)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src, "kernel_ms": fm_ms,
-                "algorithmic_bytes": int(bytes_fwd + bytes_bwd_scatter),
-                "forward_only": {"kernel": f"k_fm_fast<{k},predict> (gather+interaction, K1 of SURVEY 8d)",
-                                 "achieved": ach_fwd, "frac": ach_fwd / peak, "kernel_ms": fwd_ms,
-                                 "algorithmic_bytes": int(bytes_fwd)}}
+    roofline = {"bound": "hbm",
+                "kernel": f"k_bwd_update<{k}> (per-key gradient reduce fused with FTRL/AdaGrad; dominant kernel of the step; "
+                          "the timed stage also contains the 3 tiny InitV-pass kernels)",
+                "achieved": ach_upd, "peak": peak, "unit": "GB/s", "frac": ach_upd / peak, "traffic": None,
+                "peak_source": peak_src, "kernel_ms": upd_ms, "algorithmic_bytes": int(bytes_upd),
+                "gather_interaction": {"kernel": f"k_fm_fast<{k},predict> (gather+interaction, K1 of SURVEY 8d; validation launches)",
+                                       "achieved": ach_fwd, "frac": ach_fwd / peak, "kernel_ms": fwd_ms,
+                                       "algorithmic_bytes": int(bytes_fwd)},
+                "gather_interaction_train": {"kernel": f"k_fm_fast<{k},emit> (K1 + p*XV rows + nnz payload)",
+                                             "achieved": ach_fm, "frac": ach_fm / peak, "kernel_ms": fm_ms,
+                                             "algorithmic_bytes": int(bytes_emit)}}
     U = U_mean
     bytes_step = (bytes_fwd + (N * (4 * k + 8) + 16 * B + N * 4 * (k + 1)) + U * (4 * (k + 1) + 8 * k + 12)
                   + U * (8 * k + 12))                       # BASELINE.md section 3 full-step model

@@ -76,8 +76,8 @@ def lib():
         L.dfb_row_stride.argtypes = [vp]
         L.dfb_dev_feacnt.argtypes = [vp, vp, sz, vp]
         L.dfb_dev_pull_rows.argtypes = [vp, vp, sz, vp, vp, vp]
-        L.dfb_dev_fm_step.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp, vp]
-        L.dfb_dev_push_rows.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+        L.dfb_dev_fm_step.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp]
+        L.dfb_dev_push_rows.argtypes = [vp, vp, sz, vp, vp, vp]
         L.dfb_wait_step.argtypes = [vp, C.POINTER(Progress)]
         L.dfb_profile.argtypes = [vp, C.c_int]
         L.dfb_profile_read.argtypes = [vp, vp, vp]
@@ -265,10 +265,10 @@ class Engine:
         self._ck(self.L.dfb_profile(self.h, int(enable)))
 
     def profile_read(self):
-        ms = np.zeros(4, np.float64)
-        cnt = np.zeros(4, np.uint64)
+        ms = np.zeros(5, np.float64)
+        cnt = np.zeros(5, np.uint64)
         self._ck(self.L.dfb_profile_read(self.h, _p(ms), _p(cnt)))
-        names = ["lookup", "fm", "auc", "update"]
+        names = ["lookup", "fm", "auc", "csc", "update"]
         return {n: dict(ms=float(ms[i]), count=int(cnt[i])) for i, n in enumerate(names)}
 
     def read_progress(self):
@@ -293,10 +293,9 @@ class Engine:
     def dev_pull_rows(self, d_keys, n, d_w, d_hasv, d_V):
         self._ck(self.L.dfb_dev_pull_rows(self.h, _p(d_keys), n, _p(d_w), _p(d_hasv), _p(d_V)))
 
-    def dev_fm_step(self, nrows, nnz, d_off, d_idx, d_val, d_lab, nkeys, d_w, d_hasv, d_V, is_train, d_gw, d_gxxp,
-                    d_gV):
-        self._ck(self.L.dfb_dev_fm_step(self.h, nrows, nnz, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys, _p(d_w),
-                                        _p(d_hasv), _p(d_V), int(is_train), _p(d_gw), _p(d_gxxp), _p(d_gV)))
+    def dev_fm_step(self, nrows, nnz, d_off, d_idx, d_val, d_lab, nkeys, d_w, d_hasv, d_V, is_train, d_gw, d_gV):
+        self._ck(self.L.dfb_dev_fm_step(self.h, nrows, nnz, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys,
+                                        _p(d_w), _p(d_hasv), _p(d_V), int(is_train), _p(d_gw), _p(d_gV)))
 
-    def dev_push_rows(self, d_keys, n, d_gw, d_gxxp, d_hasv, d_gV):
-        self._ck(self.L.dfb_dev_push_rows(self.h, _p(d_keys), n, _p(d_gw), _p(d_gxxp), _p(d_hasv), _p(d_gV)))
+    def dev_push_rows(self, d_keys, n, d_gw, d_hasv, d_gV):
+        self._ck(self.L.dfb_dev_push_rows(self.h, _p(d_keys), n, _p(d_gw), _p(d_hasv), _p(d_gV)))

@@ -109,6 +109,9 @@ int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t
 int launch_grad_finalize(int V_dim, size_t nkeys, const float* weights, const int* V_pos,
                          const float* xxp, float* grad, cudaStream_t s);
 
+int launch_grad_finalize_dense(int V_dim, int ks, size_t nkeys, const int* hasv, const float* V,
+                               const float* xxp, float* gV, cudaStream_t s);
+
 // ---- launchers (kernels_table.cu) ----
 int launch_table_init(Table& t, unsigned seed, cudaStream_t s);
 // find (or insert) keys; slot_out[i] = hash position or -1.  When pull outputs are non-null also
@@ -132,10 +135,13 @@ int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* h
                        float* V_out, cudaStream_t s);
 // FTRL/AdaGrad from per-key dense gradient rows (fused path and sharded push).
 //   pull_vrow[i] >= 0 <=> the worker saw a V row at pull time (lens[i] > 1); when
-//   vrow_is_flag the actual row is taken from the entry.  gxxp == nullptr -> use gw (binary data).
+//   vrow_is_flag the actual row is taken from the entry.
+//   xxp_mode 0: gV is the complete gradient; 1: grad_V = gV - V*gxxp[i]; 2: grad_V = gV - V*gw[i]
+//   (binary data, where XXp == grad_w).
 int launch_update_dense(Table& t, const Params& p, const int* slot, const int* pull_vrow,
                         int vrow_is_flag, size_t n, const float* gw, const float* gxxp,
-                        const float* gV, int* flags, int accumulate_penalty, cudaStream_t s);
+                        const float* gV, int* flags, int accumulate_penalty, int xxp_mode,
+                        cudaStream_t s);
 // FTRL/AdaGrad from the reference's ragged gradient layout (sgd_updater.cc:74-98)
 int launch_update_ragged(Table& t, const Params& p, const int* slot, size_t n, const float* grads,
                          const int* lens_or_null, const int* pos, int* flags, cudaStream_t s);
@@ -163,13 +169,14 @@ int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t 
                      uint32_t* lidx_sorted, void* occ_sorted, int* col_start, int* col_end,
                      void* cub_tmp, size_t cub_bytes, cudaStream_t s);
 // per key: grad = sum_occ x * pXV[row] - V * XXp, then either FTRL/AdaGrad in place (apply) or
-// dense gradient rows out (gw_out/gxxp_out/gV_out, the sharded worker).
+// complete dense gradient rows out (gw_out, gV_out = sum - V_pulled*XXp; the sharded worker).
 int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,
                       const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
                       const float* p_row, const float* pxv, int* flags, int accumulate_penalty,
                       cudaStream_t s);
 int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* col_start,
                      const int* col_end, const void* occ_sorted, bool valued, const float* p_row,
-                     const float* pxv, float* gw_out, float* gxxp_out, float* gV_out, cudaStream_t s);
+                     const float* pxv, float* gw_out, const float* V_pulled, float* gV_out,
+                     cudaStream_t s);
 
 }  // namespace dfb

@@ -38,7 +38,8 @@ struct dfb_engine {
   int compute_auc = 1;
   int force_generic = 0;
   int scatter_sorted = 1;   // 1: atomic-free sorted reduction (deterministic); 0: red.global atomics
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_fm_done = nullptr, ev_auc_done = nullptr;
   Table tab;
   std::string err;
   std::vector<std::pair<std::string, std::string>> unknown;
@@ -46,7 +47,7 @@ struct dfb_engine {
 
   // workspaces (grown on demand)
   DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
-  DevBuf auc_k, auc_v;
+  DevBuf auc_k, auc_v, auc_tmp;
   DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
   DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
   DevBuf scal, hasv, rV, rcg, nvals;
@@ -60,14 +61,14 @@ struct dfb_engine {
   uint64_t submitted = 0, collected = 0;
   DevProgress backlog;             // snapshots folded in when the ring was full
   // optional per-stage CUDA-event timing (bench.py's roofline numbers)
-  static constexpr int kStages = 4;      // lookup+pull, fm, auc, update(+initv)
+  static constexpr int kStages = 5;      // lookup+pull, fm, auc, csc sort, update(+initv)
   static constexpr int kProfRing = 32;
   int profile = 0;
   std::vector<cudaEvent_t> pev;          // [kProfRing][kStages][2]
   std::vector<char> pev_used;            // [kProfRing][kStages]
   uint64_t prof_steps = 0;
-  double stage_ms[kStages] = {0, 0, 0, 0};
-  uint64_t stage_n[kStages] = {0, 0, 0, 0};
+  double stage_ms[kStages] = {0, 0, 0, 0, 0};
+  uint64_t stage_n[kStages] = {0, 0, 0, 0, 0};
   DevProgress* h_prog = nullptr;   // pinned
   unsigned long long* h_nvals = nullptr;  // pinned
 
@@ -318,22 +319,36 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
     h->launches += nl;
   }
+  bool auc_pending = false;
   if (h->compute_auc && nrows) {
+    // AUC depends only on pred: run it on the auxiliary stream, overlapped with the gradient
+    // reduction / update below (when profiling, keep it on the main stream so that it is timed)
     DFB_TRY(h->ensure(h->auc_k, nrows * sizeof(float)));
     DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
-    size_t sb = sort_tmp_bytes(nrows);
-    if (sb > h->cub.bytes) DFB_TRY(h->ensure(h->cub, sb));
+    DFB_TRY(h->ensure(h->auc_tmp, sort_tmp_bytes(nrows)));
+    cudaStream_t as = h->profile ? s : h->aux_stream;
+    if (!h->profile) {
+      DFB_CUDA(h, cudaEventRecord(h->ev_fm_done, s));
+      DFB_CUDA(h, cudaStreamWaitEvent(as, h->ev_fm_done, 0));
+    }
     StageTimer tm(h, 2);
     h->launches += launch_auc(d_lab, h->pred.as<float>(), nrows, nullptr, nullptr, h->auc_k.as<float>(),
-                              h->auc_v.as<float>(), h->cub.p, h->cub.bytes, &h->tab.prog->auc, s);
+                              h->auc_v.as<float>(), h->auc_tmp.p, h->auc_tmp.bytes, &h->tab.prog->auc, as);
+    if (!h->profile) {
+      DFB_CUDA(h, cudaEventRecord(h->ev_auc_done, as));
+      auc_pending = true;
+    }
   }
-  StageTimer tm_upd(h, 3);
   if (sorted) {
     // CalcGrad + Push(kGradient) without materialising the gradient: CSC view of the batch, then
     // per key reduce + FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
+    StageTimer tm(h, 3);
     h->launches += launch_csc_build(d_idx, h->occ.p, d_val != nullptr, nnz, U, h->lidx_sorted.as<uint32_t>(),
                                     h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
                                     h->cub.bytes, s);
+  }
+  StageTimer tm_upd(h, 4);
+  if (sorted) {
     int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U, h->col_start.as<int>(), h->col_end.as<int>(),
                                h->occ_sorted.p, d_val != nullptr, h->p_row.as<float>(), h->pxv.as<float>(), flags,
                                1, s);
@@ -343,7 +358,8 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   } else if (is_train) {
     // Push(kGradient): FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
     h->launches += launch_update_dense(h->tab, h->prm, slot, u_vrow, 0, U, h->gw.as<float>(),
-                                       d_val ? h->gxxp.as<float>() : nullptr, h->gV.as<float>(), flags, 1, s);
+                                       d_val ? h->gxxp.as<float>() : nullptr, h->gV.as<float>(), flags, 1,
+                                       d_val ? 1 : 2, s);
     h->launches += launch_initv(h->tab, h->prm, slot, U, flags, pos, h->cub.p, h->cub.bytes, s);
   } else {
     h->launches += launch_penalty(h->prm, h->tab.prog, u_w, u_vrow, h->tab.V, h->tab.rs, 0, U, s);
@@ -352,6 +368,7 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
     tm_upd.~StageTimer(); tm_upd.e = nullptr;
     h->prof_steps++;
   }
+  if (auc_pending) DFB_CUDA(h, cudaStreamWaitEvent(s, h->ev_auc_done, 0));
   DFB_CUDA(h, cudaGetLastError());
   return 0;
 }
@@ -442,6 +459,9 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) return cfail("cudaSetDevice");
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
+  if ((e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
+  if ((e = cudaEventCreateWithFlags(&h->ev_fm_done, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
+  if ((e = cudaEventCreateWithFlags(&h->ev_auc_done, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
   for (auto& s : h->in) {
     if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
@@ -482,7 +502,7 @@ int dfb_destroy(dfb_handle h) {
   if (!h) return DFB_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
+  DevBuf* bufs[] = {&h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
                     &h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
                     &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
                     &h->a_val, &h->a_lab, &h->a_w, &h->a_wpos, &h->a_vpos, &h->a_pred, &h->a_grad, &h->scal,
@@ -505,6 +525,9 @@ int dfb_destroy(dfb_handle h) {
   for (auto& ev : h->pev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fm_done) cudaEventDestroy(h->ev_fm_done);
+  if (h->ev_auc_done) cudaEventDestroy(h->ev_auc_done);
   delete h;
   return DFB_OK;
 }
@@ -979,28 +1002,33 @@ int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w
 
 int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
                     const float* d_value, const float* d_label, size_t nkeys, const float* d_w, const int* d_hasv,
-                    const float* d_V, int is_train, float* d_gw_out, float* d_gxxp_out, float* d_gV_out) {
+                    const float* d_V, int is_train, float* d_gw_out, float* d_gV_out) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const int ks = h->tab.ks, k = h->prm.V_dim;
+  if (nkeys > 0x7fffffffULL || nrows > 0x7fffffffULL || nnz > 0x7fffffffULL)
+    return h->fail(DFB_ERR_INVALID, "batch too large");
   const bool sorted = is_train && h->scatter_sorted && !h->force_generic && fm_fast_supported(k) && ks == k;
   DFB_TRY(h->ensure(h->pred, nrows * sizeof(float)));
   FmView v;
   memset(&v, 0, sizeof(v));
   v.wbase = d_w; v.w_pos = nullptr;
   v.vbase = d_V; v.v_pos = d_hasv; v.vstride = ks; v.dense = 1;
+  float* gxxp = nullptr;
   if (is_train) {
-    if (!d_gw_out || (k > 0 && !d_gV_out) || (k > 0 && d_value && !d_gxxp_out))
-      return h->fail(DFB_ERR_INVALID, "gradient outputs are NULL");
+    if (!d_gw_out || (k > 0 && !d_gV_out)) return h->fail(DFB_ERR_INVALID, "gradient outputs are NULL");
     if (sorted) {
       DFB_TRY(ensure_sorted_ws(h, nrows, nnz, nkeys, d_value != nullptr));
     } else {
       DFB_CUDA(h, cudaMemsetAsync(d_gw_out, 0, nkeys * sizeof(float), s));
       if (k > 0) DFB_CUDA(h, cudaMemsetAsync(d_gV_out, 0, nkeys * (size_t)ks * sizeof(float), s));
-      if (k > 0 && d_gxxp_out) DFB_CUDA(h, cudaMemsetAsync(d_gxxp_out, 0, nkeys * sizeof(float), s));
-      v.gwbase = d_gw_out; v.gvbase = d_gV_out; v.gvstride = ks;
-      v.gxxp = (k > 0 && d_value) ? d_gxxp_out : nullptr;
+      if (k > 0 && d_value) {
+        DFB_TRY(h->ensure(h->gxxp, nkeys * sizeof(float)));
+        DFB_CUDA(h, cudaMemsetAsync(h->gxxp.p, 0, nkeys * sizeof(float), s));
+        gxxp = h->gxxp.as<float>();
+      }
+      v.gwbase = d_gw_out; v.gvbase = d_gV_out; v.gvstride = ks; v.gxxp = gxxp;
     }
   }
   FmBatch b;
@@ -1021,17 +1049,20 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_of
                                     h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
                                     h->cub.bytes, s);
     int nl = launch_bwd_dense(k, ks, d_hasv, nkeys, h->col_start.as<int>(), h->col_end.as<int>(), h->occ_sorted.p,
-                              d_value != nullptr, h->p_row.as<float>(), h->pxv.as<float>(), d_gw_out,
-                              d_value ? d_gxxp_out : nullptr, d_gV_out, s);
+                              d_value != nullptr, h->p_row.as<float>(), h->pxv.as<float>(), d_gw_out, d_V, d_gV_out,
+                              s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
     h->launches += nl;
+  } else if (is_train && k > 0) {
+    // grad_V -= V_pulled * XXp (XXp == grad_w for binary data): the worker ships complete gradients
+    h->launches += launch_grad_finalize_dense(k, ks, nkeys, d_hasv, d_V, gxxp ? gxxp : d_gw_out, d_gV_out, s);
   }
   if (h->compute_auc && nrows) {
     DFB_TRY(h->ensure(h->auc_k, nrows * sizeof(float)));
     DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
-    DFB_TRY(h->ensure(h->cub, sort_tmp_bytes(nrows)));
+    DFB_TRY(h->ensure(h->auc_tmp, sort_tmp_bytes(nrows)));
     h->launches += launch_auc(d_label, h->pred.as<float>(), nrows, nullptr, nullptr, h->auc_k.as<float>(),
-                              h->auc_v.as<float>(), h->cub.p, h->cub.bytes, &h->tab.prog->auc, s);
+                              h->auc_v.as<float>(), h->auc_tmp.p, h->auc_tmp.bytes, &h->tab.prog->auc, s);
   }
   // the worker evaluates the penalty of what it pulled (sgd_learner.cc:148)
   h->launches += launch_penalty(h->prm, h->tab.prog, d_w, d_hasv, d_V, ks, 1, nkeys, s);
@@ -1039,16 +1070,16 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_of
   return DFB_OK;
 }
 
-int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_gw, const float* d_gxxp,
-                      const int* d_hasv, const float* d_gV) {
+int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_gw, const int* d_hasv,
+                      const float* d_gV) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
   h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
-  h->launches += launch_update_dense(h->tab, h->prm, h->slot.as<int>(), d_hasv, 1, n, d_gw, d_gxxp, d_gV,
-                                     h->flags.as<int>(), 0, s);
+  h->launches += launch_update_dense(h->tab, h->prm, h->slot.as<int>(), d_hasv, 1, n, d_gw, nullptr, d_gV,
+                                     h->flags.as<int>(), 0, 0, s);
   h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, h->flags.as<int>(), h->pos.as<int>(),
                               h->cub.p, h->cub.bytes, s);
   DFB_CUDA(h, cudaGetLastError());

@@ -320,6 +320,19 @@ __global__ void k_grad_finalize(int k, size_t nkeys, const float* weights, const
   }
 }
 
+// dense pulled layout: gV[u][ks] -= V[u][ks] * xxp[u] for keys with a V row (fm_loss.h:181-188)
+__global__ void k_grad_finalize_dense(int k, int ks, size_t nkeys, const int* hasv, const float* V,
+                                      const float* xxp, float* gV) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t u = warp0; u < nkeys; u += nwarps) {
+    if (hasv[u] < 0) continue;
+    const float s = xxp[u];
+    for (int l = lane; l < k; l += 32) gV[u * (size_t)ks + l] -= V[u * (size_t)ks + l] * s;
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int K>
@@ -377,6 +390,15 @@ int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t
       cudaFuncSetAttribute(k_fm_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_fm_generic<false><<<grid, threads, smem, s>>>(b, v);
   }
+  return 1;
+}
+
+int launch_grad_finalize_dense(int V_dim, int ks, size_t nkeys, const int* hasv, const float* V,
+                               const float* xxp, float* gV, cudaStream_t s) {
+  if (V_dim == 0 || nkeys == 0) return 0;
+  size_t need = (nkeys + 7) / 8;
+  int grid = (int)(need < (size_t)(148 * 8) ? need : (size_t)(148 * 8));
+  k_grad_finalize_dense<<<grid, 256, 0, s>>>(V_dim, ks, nkeys, hasv, V, xxp, gV);
   return 1;
 }
 

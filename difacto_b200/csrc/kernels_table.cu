@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_update_fast(Table t, Params p, const in
                                                      size_t n, const float* __restrict__ gw,
                                                      const float* __restrict__ gxxp,
                                                      const float* __restrict__ gV, int* __restrict__ flags,
-                                                     int acc_pen) {
+                                                     int acc_pen, int xxp_mode) {
   constexpr int LPR = K / 4;
   constexpr int G = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) k_update_fast(Table t, Params p, const in
       flags[i] = (became_nz && p.V_dim > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
     }
     if (vr >= 0) {
-      const float xxp = gxxp ? gxxp[i] : g_w;
+      const float xxp = xxp_mode == 0 ? 0.f : (xxp_mode == 1 ? gxxp[i] : g_w);
       float* Vr = t.V + (size_t)vr * t.rs + sub * 4;
       float* Cr = t.Vcg + (size_t)vr * t.rs + sub * 4;
       float4 v = *reinterpret_cast<const float4*>(Vr);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) k_update_dense_generic(Table t, Params p,
                                                               const float* __restrict__ gw,
                                                               const float* __restrict__ gxxp,
                                                               const float* __restrict__ gV,
-                                                              int* __restrict__ flags, int acc_pen) {
+                                                              int* __restrict__ flags, int acc_pen, int xxp_mode) {
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_update_dense_generic(Table t, Params p,
       flags[i] = (became_nz && k > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
     }
     if (vr >= 0) {
-      const float xxp = gxxp ? gxxp[i] : g_w;
+      const float xxp = xxp_mode == 0 ? 0.f : (xxp_mode == 1 ? gxxp[i] : g_w);
       float* Vr = t.V + (size_t)vr * t.rs;
       float* Cr = t.Vcg + (size_t)vr * t.rs;
       const float* g = gV + i * (size_t)t.ks;
@@ -554,6 +554,11 @@ __device__ __forceinline__ void load_occ(const void* occ, int o, uint32_t& row, 
 // (fm_loss.h:164-198, summed in row order like SpMM::TransTimes), immediately consumed by
 // FTRL (w) and AdaGrad (V): the gradient never exists in HBM.  APPLY=false writes the dense
 // gradient rows instead (worker side of the sharded store).
+//
+// A warp owns 32 consecutive keys.  Phase A is lane-parallel (one key per lane): coalesced
+// metadata loads, 32 independent entry sectors in flight, the scalar reductions and FTRL.
+// Phase B walks the 32 keys G at a time with LPR lanes (one float4 each) per 8K-byte table row,
+// UNRB row-groups in flight; the first occurrence's p*XV row is fetched together with V|cg.
 template <int K, bool HAS_VAL, bool APPLY>
 __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int* __restrict__ slot,
                                                     const int* __restrict__ pull_vrow, size_t n,
@@ -563,68 +568,118 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
                                                     const float* __restrict__ p_row,
                                                     const float* __restrict__ pxv, int* __restrict__ flags,
                                                     int acc_pen, float* __restrict__ gw_out,
-                                                    float* __restrict__ gxxp_out, float* __restrict__ gV_out) {
+                                                    const float* __restrict__ V_pulled,
+                                                    float* __restrict__ gV_out) {
   constexpr int LPR = K / 4;
   constexpr int G = 32 / LPR;
+  constexpr int NPASS = 32 / G;
+  constexpr int UNRB = NPASS >= 2 ? 2 : 1;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   float pen = 0.f;
-  for (size_t base = warp0 * G; base < n; base += nwarps * G) {
-    const size_t i = base + grp;
-    if (i >= n) continue;
-    int s = 0;
-    int vr = pull_vrow[i];
-    Entry* e = nullptr;
-    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), v = sc, c = sc;
-    float* Vr = nullptr;
-    if (APPLY) {
-      s = slot[i];
-      if (s < 0) { if (sub == 0) flags[i] = 0; continue; }
-      e = &t.tab[s];
-      // the table loads do not depend on the occurrence list: issue them first
-      if (sub == 0) sc = *reinterpret_cast<const float4*>(&e->fea_cnt);
-      if (vr >= 0) {
-        Vr = t.V + (size_t)vr * t.rs + sub * 4;
-        v = *reinterpret_cast<const float4*>(Vr);
-        c = *reinterpret_cast<const float4*>(Vr + t.ks);
-      }
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    // ---------------- phase A: one key per lane ----------------
+    const size_t i = base + lane;
+    const bool active = i < n;
+    int s = -1, vr = -1, o0 = 0, o1 = 0;
+    if (active) {
+      vr = pull_vrow[i];
+      o0 = col_start[i];
+      o1 = col_end[i];
+      if (APPLY) s = slot[i];
     }
-    const int o0 = col_start[i], o1 = col_end[i];
-    float gw = 0.f, xxp = 0.f;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    Entry* e = nullptr;
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (APPLY && s >= 0) {
+      e = &t.tab[s];
+      sc = *reinterpret_cast<const float4*>(&e->fea_cnt);
+    }
+    float gw = 0.f, xxp = 0.f, x0 = 0.f;
+    uint32_t row0 = 0;
     for (int o = o0; o < o1; ++o) {
       uint32_t row; float x;
       load_occ<HAS_VAL>(occ, o, row, x);
       const float pr = __ldg(p_row + row);
       gw = __fadd_rn(gw, __fmul_rn(pr, x));                        // spmv.h:162-164
       if (HAS_VAL) xxp = __fadd_rn(xxp, __fmul_rn(pr, __fmul_rn(x, x)));
-      if (vr >= 0) {
-        const float4 tt = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)row * K + sub * 4));
-        g.x = __fadd_rn(g.x, __fmul_rn(tt.x, x)); g.y = __fadd_rn(g.y, __fmul_rn(tt.y, x));   // spmm.h:152-154
-        g.z = __fadd_rn(g.z, __fmul_rn(tt.z, x)); g.w = __fadd_rn(g.w, __fmul_rn(tt.w, x));
-      }
+      if (o == o0) { row0 = row; x0 = x; }
     }
     if (!HAS_VAL) xxp = gw;
     if (APPLY) {
-      if (sub == 0) {
+      if (s >= 0) {
         if (acc_pen) pen += pen_w(p, sc.y);
         const bool became_nz = ftrl_step(p, gw, sc.y, sc.z, sc.w);
         *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
         flags[i] = (became_nz && p.V_dim > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
+      } else if (active) {
+        flags[i] = 0;
       }
-      if (vr >= 0) {
-        if (acc_pen) pen += 0.5f * p.V_l2 * (v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
-        adagrad_step(p, __fsub_rn(g.x, __fmul_rn(v.x, xxp)), v.x, c.x);
-        adagrad_step(p, __fsub_rn(g.y, __fmul_rn(v.y, xxp)), v.y, c.y);
-        adagrad_step(p, __fsub_rn(g.z, __fmul_rn(v.z, xxp)), v.z, c.z);
-        adagrad_step(p, __fsub_rn(g.w, __fmul_rn(v.w, xxp)), v.w, c.w);
-        *reinterpret_cast<float4*>(Vr) = v;
-        *reinterpret_cast<float4*>(Vr + t.ks) = c;
+      if (s < 0) vr = -1;
+    } else if (active) {
+      gw_out[i] = gw;
+    }
+    // ---------------- phase B: the table rows, G keys per pass ----------------
+#pragma unroll 1
+    for (int pass = 0; pass < NPASS; pass += UNRB) {
+      float4 v[UNRB], c[UNRB], g[UNRB];
+      int vrk[UNRB], o0k[UNRB], o1k[UNRB];
+      float xxpk[UNRB];
+#pragma unroll
+      for (int q = 0; q < UNRB; ++q) {
+        const int kk = (pass + q) * G + grp;
+        vrk[q] = __shfl_sync(kFull, vr, kk);
+        o0k[q] = __shfl_sync(kFull, o0, kk);
+        o1k[q] = __shfl_sync(kFull, o1, kk);
+        xxpk[q] = __shfl_sync(kFull, xxp, kk);
+        const uint32_t r0 = __shfl_sync(kFull, row0, kk);
+        const float xx0 = __shfl_sync(kFull, x0, kk);
+        v[q] = c[q] = g[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vrk[q] >= 0) {
+          if (APPLY) {
+            const float* Vr = t.V + (size_t)vrk[q] * t.rs + sub * 4;
+            v[q] = *reinterpret_cast<const float4*>(Vr);
+            c[q] = *reinterpret_cast<const float4*>(Vr + t.ks);
+          } else {
+            // the pulled row (dense [n][K] buffer): the worker applies "- V * XXp" itself (fm_loss.h:181-188)
+            const size_t ik = base + (size_t)((pass + q) * G + grp);
+            v[q] = __ldg(reinterpret_cast<const float4*>(V_pulled + ik * (size_t)K + sub * 4));
+          }
+          if (o1k[q] > o0k[q]) {
+            const float4 tt = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)r0 * K + sub * 4));
+            g[q] = make_float4(__fmul_rn(tt.x, xx0), __fmul_rn(tt.y, xx0), __fmul_rn(tt.z, xx0),
+                               __fmul_rn(tt.w, xx0));                                   // spmm.h:152-154
+          }
+        }
       }
-    } else {
-      if (sub == 0) { gw_out[i] = gw; if (gxxp_out) gxxp_out[i] = xxp; }
-      if (vr >= 0) *reinterpret_cast<float4*>(gV_out + i * (size_t)K + sub * 4) = g;
+#pragma unroll
+      for (int q = 0; q < UNRB; ++q) {
+        if (vrk[q] < 0) continue;
+        for (int o = o0k[q] + 1; o < o1k[q]; ++o) {     // further occurrences, still in row order
+          uint32_t row; float x;
+          load_occ<HAS_VAL>(occ, o, row, x);
+          const float4 tt = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)row * K + sub * 4));
+          g[q].x = __fadd_rn(g[q].x, __fmul_rn(tt.x, x)); g[q].y = __fadd_rn(g[q].y, __fmul_rn(tt.y, x));
+          g[q].z = __fadd_rn(g[q].z, __fmul_rn(tt.z, x)); g[q].w = __fadd_rn(g[q].w, __fmul_rn(tt.w, x));
+        }
+        if (APPLY) {
+          if (acc_pen) pen += 0.5f * p.V_l2 * (v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w);
+          const float xp = xxpk[q];
+          adagrad_step(p, __fsub_rn(g[q].x, __fmul_rn(v[q].x, xp)), v[q].x, c[q].x);
+          adagrad_step(p, __fsub_rn(g[q].y, __fmul_rn(v[q].y, xp)), v[q].y, c[q].y);
+          adagrad_step(p, __fsub_rn(g[q].z, __fmul_rn(v[q].z, xp)), v[q].z, c[q].z);
+          adagrad_step(p, __fsub_rn(g[q].w, __fmul_rn(v[q].w, xp)), v[q].w, c[q].w);
+          float* Vr = t.V + (size_t)vrk[q] * t.rs + sub * 4;
+          *reinterpret_cast<float4*>(Vr) = v[q];
+          *reinterpret_cast<float4*>(Vr + t.ks) = c[q];
+        } else {
+          const size_t ik = base + (size_t)((pass + q) * G + grp);
+          const float xp = xxpk[q];
+          *reinterpret_cast<float4*>(gV_out + ik * (size_t)K + sub * 4) =
+              make_float4(__fsub_rn(g[q].x, __fmul_rn(v[q].x, xp)), __fsub_rn(g[q].y, __fmul_rn(v[q].y, xp)),
+                          __fsub_rn(g[q].z, __fmul_rn(v[q].z, xp)), __fsub_rn(g[q].w, __fmul_rn(v[q].w, xp)));
+        }
+      }
     }
   }
   if (APPLY && acc_pen) {
@@ -720,12 +775,12 @@ int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* h
 
 int launch_update_dense(Table& t, const Params& p, const int* slot, const int* pull_vrow, int vrow_is_flag,
                         size_t n, const float* gw, const float* gxxp, const float* gV, int* flags,
-                        int acc_pen, cudaStream_t s) {
+                        int acc_pen, int xxp_mode, cudaStream_t s) {
   if (n == 0) return 0;
   const int k = p.V_dim;
 #define DFB_UPD(K)                                                                                   \
   k_update_fast<K><<<grid_warps((n + (32 / (K / 4)) - 1) / (32 / (K / 4)), 8, 148 * 8), 256, 0, s>>>( \
-      t, p, slot, pull_vrow, vrow_is_flag, n, gw, gxxp, gV, flags, acc_pen)
+      t, p, slot, pull_vrow, vrow_is_flag, n, gw, gxxp, gV, flags, acc_pen, xxp_mode)
   switch (k) {
     case 8: DFB_UPD(8); return 1;
     case 16: DFB_UPD(16); return 1;
@@ -736,7 +791,7 @@ int launch_update_dense(Table& t, const Params& p, const int* slot, const int* p
   }
 #undef DFB_UPD
   k_update_dense_generic<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, p, slot, pull_vrow, vrow_is_flag, n, gw,
-                                                                  gxxp, gV, flags, acc_pen);
+                                                                  gxxp, gV, flags, acc_pen, xxp_mode);
   return 1;
 }
 
@@ -816,7 +871,7 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
   if (n == 0) return 0;
 #define DFB_BU(K)                                                                                          \
   do {                                                                                                     \
-    const int grid = grid_warps((n + (32 / (K / 4)) - 1) / (32 / (K / 4)), 8, 148 * 8);                      \
+    const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
     if (valued) k_bwd_update<K, true, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end, \
                    occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr);                      \
     else k_bwd_update<K, false, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end,     \
@@ -835,7 +890,7 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
 
 int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* col_start, const int* col_end,
                      const void* occ_sorted, bool valued, const float* p_row, const float* pxv, float* gw_out,
-                     float* gxxp_out, float* gV_out, cudaStream_t s) {
+                     const float* V_pulled, float* gV_out, cudaStream_t s) {
   if (n == 0) return 0;
   if (ks != V_dim) return -1;
   Table t;
@@ -844,11 +899,11 @@ int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* co
   p.V_dim = V_dim;
 #define DFB_BD(K)                                                                                          \
   do {                                                                                                     \
-    const int grid = grid_warps((n + (32 / (K / 4)) - 1) / (32 / (K / 4)), 8, 148 * 8);                      \
+    const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
     if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, nullptr, hasv, n, col_start, col_end, \
-                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, gxxp_out, gV_out);                           \
+                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, V_pulled, gV_out);                           \
     else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, nullptr, hasv, n, col_start, col_end,      \
-                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, gxxp_out, gV_out);                           \
+                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, V_pulled, gV_out);                           \
   } while (0)
   switch (V_dim) {
     case 8: DFB_BD(8); return 1;

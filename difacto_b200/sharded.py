@@ -1,0 +1,282 @@
+"""NVLink-sharded model store: difacto's Store::Pull/Push as NCCL all-to-all of the active rows.
+
+The reference shards keys over ps-lite servers by contiguous ranges of the (reversed) key space
+(ps-lite/src/postoffice.cc:127-136) and a worker slices its sorted key list per server
+(ps-lite/include/ps/kv_app.h:406-460, DefaultSlicer); difacto's own distributed Store is
+`LOG(FATAL) << "not implemented"` (src/store/store.cc:9-11).  Here every rank is both a worker (its
+own minibatch) and a server (shard `rank` of the table, one difacto_b200 engine), one process per
+GPU, `torch.distributed` for the plumbing:
+
+    counts      all_to_all of the per-owner segment sizes                    (S ints)
+    keys        all_to_all_v of the sorted key segments                      (8 B / key)
+    [feacnt]    all_to_all_v of the counts; owner applies Update(kFeaCount) per source rank
+    Pull        owner gathers {w, has_V, V[ks]} rows (dfb_dev_pull_rows) -> all_to_all_v back
+    compute     dfb_dev_fm_step on the pulled dense rows: loss/AUC/penalty + complete gradients
+    Push        all_to_all_v of {gw, gV[ks]} -> owner applies FTRL/AdaGrad per source rank, in
+                rank order (the reference applies every worker's push as a separate Update in
+                arrival order, sgd_updater.cc:74-98; rank order makes it deterministic)
+
+Because the batch's keys are sorted, every owner's keys are ONE contiguous segment, so the
+concatenation of what comes back from owners 0..S-1 is already in key order: no permutation pass.
+
+The protocol is backend-agnostic: `CudaBackend` drives the sm_100a engine (the product);
+tests/ injects a CPU backend over gloo to check the protocol itself against the oracle.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def key_owner_np(keys, S):
+    """vectorised dfb_key_owner: min(S-1, key // (UINT64_MAX // S)) on reversed keys"""
+    keys = np.asarray(keys, dtype=np.uint64)
+    width = np.uint64(0xFFFFFFFFFFFFFFFF // S)
+    return np.minimum(keys // width, np.uint64(S - 1)).astype(np.int64)
+
+
+def shard_bounds_np(sorted_keys, S):
+    """segment boundaries [S+1] of a sorted key array (DefaultSlicer's lower_bound per range)"""
+    keys = np.asarray(sorted_keys, dtype=np.uint64)
+    width = 0xFFFFFFFFFFFFFFFF // S
+    cuts = np.array([width * i for i in range(1, S)], dtype=np.uint64)
+    inner = np.searchsorted(keys, cuts, side="left")
+    return np.concatenate([[0], inner, [len(keys)]]).astype(np.int64)
+
+
+class CudaBackend:
+    """one shard = one difacto_b200 engine; all arrays are torch CUDA tensors"""
+
+    def __init__(self, engine, device):
+        self.E = engine
+        self.device = device
+        self.ks = engine.row_stride()
+        self.V_dim = engine.V_dim
+        self.stream = torch.cuda.ExternalStream(engine.stream(), device=device)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def feacnt(self, keys, cnt):
+        if len(keys):
+            self.E.dev_feacnt(keys, len(keys), cnt)
+
+    def pull_rows(self, keys, w, hasv, V):
+        if len(keys):
+            self.E.dev_pull_rows(keys, len(keys), w, hasv, V)
+
+    def fm_step(self, batch, w, hasv, V, is_train, gw, gV):
+        self.E.dev_fm_step(batch["nrows"], batch["nnz"], batch["off"], batch["lidx"], batch.get("val"),
+                           batch["lab"], batch["U"], w, hasv, V, is_train, gw, gV)
+
+    def push_rows(self, keys, gw, hasv, gV):
+        if len(keys):
+            self.E.dev_push_rows(keys, len(keys), gw, hasv, gV)
+
+    def read_progress(self):
+        return self.E.read_progress()
+
+
+class ShardedStore:
+    """Store + the worker's minibatch step over S ranks"""
+
+    def __init__(self, backend, group=None):
+        self.b = backend
+        self.group = group
+        self.S = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ks = backend.ks
+        self._buf = {}
+        self.timers = None
+
+    def _get(self, name, n, shape_tail, dtype):
+        t = self._buf.get(name)
+        need = (n,) + shape_tail
+        if t is None or t.shape[0] < n or t.dtype != dtype:
+            cap = max(int(n * 1.2) + 16, 16)
+            t = self.b.empty((cap,) + shape_tail, dtype)
+            self._buf[name] = t
+        return t[:n]
+
+    def _a2a(self, out, inp, out_splits, in_splits):
+        if self.S == 1:
+            out.copy_(inp)
+        else:
+            dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
+
+    def step(self, batch, is_train=True, push_cnt=False):
+        """one minibatch of SGDLearner::IterateData on this rank's batch; collective over ranks.
+
+        batch: dict(nrows, nnz, U, off, lidx, val|None, lab, keys, cnt|None, bounds[S+1])"""
+        S, U, ks = self.S, batch["U"], self.ks
+        bounds = batch["bounds"]
+        send = [int(bounds[i + 1] - bounds[i]) for i in range(S)]
+        if S == 1:
+            recv = list(send)
+        else:
+            t_send = torch.tensor(send, dtype=torch.int64, device=batch["keys"].device)
+            t_recv = torch.empty_like(t_send)
+            dist.all_to_all_single(t_recv, t_send, group=self.group)
+            recv = [int(x) for x in t_recv.tolist()]
+        R = sum(recv)
+        seg = np.concatenate([[0], np.cumsum(recv)]).astype(np.int64)
+        keys_r = self._get("keys_r", R, (), torch.int64)
+        self._a2a(keys_r, batch["keys"], recv, send)
+        if push_cnt:
+            cnt_r = self._get("cnt_r", R, (), torch.float32)
+            self._a2a(cnt_r, batch["cnt"], recv, send)
+            for src in range(S):    # one Update(kFeaCount) per worker, rank order
+                a, b = int(seg[src]), int(seg[src + 1])
+                self.b.feacnt(keys_r[a:b], cnt_r[a:b])
+        # ---- Pull ----
+        w_r = self._get("w_r", R, (), torch.float32)
+        hasv_r = self._get("hasv_r", R, (), torch.int32)
+        V_r = self._get("V_r", R, (ks,), torch.float32)
+        self.b.pull_rows(keys_r, w_r, hasv_r, V_r)
+        w = self._get("w", U, (), torch.float32)
+        hasv = self._get("hasv", U, (), torch.int32)
+        V = self._get("V", U, (ks,), torch.float32)
+        self._a2a(w, w_r, send, recv)
+        self._a2a(hasv, hasv_r, send, recv)
+        if ks:
+            self._a2a(V, V_r, send, recv)
+        # ---- Predict / Evaluate / CalcGrad ----
+        gw = self._get("gw", U, (), torch.float32)
+        gV = self._get("gV", U, (ks,), torch.float32)
+        self.b.fm_step(batch, w, hasv, V, is_train, gw, gV)
+        if not is_train:
+            return
+        # ---- Push(kGradient) ----
+        gw_r = self._get("gw_r", R, (), torch.float32)
+        gV_r = self._get("gV_r", R, (ks,), torch.float32)
+        self._a2a(gw_r, gw, recv, send)
+        if ks:
+            self._a2a(gV_r, gV, recv, send)
+        for src in range(S):        # one Update(kGradient) per worker, rank order
+            a, b = int(seg[src]), int(seg[src + 1])
+            self.b.push_rows(keys_r[a:b], gw_r[a:b], hasv_r[a:b], gV_r[a:b])
+
+
+# ---------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): one process per GPU, launched by torch.distributed.run
+# ---------------------------------------------------------------------------------------------
+def bench_main(args, rank, world, local_rank, benchmod):
+    import json
+    from difacto_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    kw = benchmod.hyper(args)
+    nb = args.working_set
+    nnz = args.nnz if args.workload == "synthetic" else 39
+    B = args.batch
+    N = B * nnz
+
+    # per-rank synthetic batches (data parallel: every rank has its own file part, sgd_learner.cc:78-89)
+    host = []
+    for b in range(nb):
+        off, lab, ids = benchmod.gen_raw_batch(args, 1 + b + 1000 * rank)
+        lidx, keys, cnt = benchmod.localize_np(ids)
+        host.append(dict(nrows=B, nnz=N, U=len(keys), bounds=shard_bounds_np(keys, world),
+                         off=torch.from_numpy(off.view(np.int64)).pin_memory(),
+                         lab=torch.from_numpy(lab).pin_memory(),
+                         lidx=torch.from_numpy(lidx.view(np.int32)).pin_memory(),
+                         keys=torch.from_numpy(keys.view(np.int64)).pin_memory(),
+                         cnt=torch.from_numpy(cnt).pin_memory()))
+    U_mean = float(np.mean([h["U"] for h in host]))
+    # this shard sees about (all ranks' keys) / world distinct keys
+    cap = int(nb * U_mean * 1.15) + 4096
+    E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap, **kw)
+    backend = CudaBackend(E, dev)
+    store = ShardedStore(backend)
+
+    def to_dev(h):
+        d = dict(h)
+        for k in ("off", "lab", "lidx", "keys", "cnt"):
+            d[k] = h[k].to(dev, non_blocking=True)
+        return d
+
+    devb = [to_dev(h) for h in host]
+    torch.cuda.synchronize()
+
+    with torch.cuda.stream(backend.stream):
+        for p in range(2):      # table warm-up: afterwards every key owns a V row
+            for b in range(nb):
+                store.step(devb[b], True, push_cnt=(p == 0))
+        E.read_progress()
+        for t in range(args.warmup):
+            store.step(devb[t % nb], True)
+        E.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = E.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = benchmod.ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        wall0 = time.time()
+        ev0.record(backend.stream)
+        for t in range(args.steps):
+            store.step(devb[(args.warmup + t) % nb], True)
+        ev1.record(backend.stream)
+        E.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        wall1 = time.time()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        launches = E.launch_count() - launches0
+        prog = E.read_progress()
+
+        # ---- e2e: per-step H2D of the localized batch from pinned memory + Progress read back ----
+        e2e = None
+        if not args.no_e2e:
+            for t in range(args.warmup):
+                store.step(to_dev(host[t % nb]), True)
+            E.read_progress()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            loss_sum = 0.0
+            for t in range(args.steps):
+                store.step(to_dev(host[(args.warmup + t) % nb]), True)
+                loss_sum += E.read_progress().loss
+            torch.cuda.synchronize()
+            dist.barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item())
+            h2d = (B + 1) * 8 + N * 4 + B * 4 + int(U_mean) * 8
+            e2e = {"value": args.steps * B * world / dt, "unit": "examples/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": 64, "ms_per_step": dt / args.steps * 1e3,
+                   "api": "ShardedStore.step (torch.distributed all_to_all + C-ABI dfb_dev_*), localized CSR + keys "
+                          "from pinned host memory every step"}
+    if rank == 0:
+        sampler.stop()
+        k = args.vdim
+        a2a_bytes = 2 * U_mean * (world - 1) / world * (8 + 4 * (k + 1))     # BASELINE.md section 3, per direction
+        nvl = 770.0   # measured peer copy GB/s per direction (B200_PROFILING.md)
+        line = {
+            "metric": benchmod.metric_name(args), "value": args.steps * B * world / (ms * 1e-3), "unit": "examples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": benchmod.workload_config(args, {
+                "unique_keys_per_batch": int(U_mean), "working_set_batches": nb,
+                "parallelism": f"dp{world} minibatches x table sharded by reversed-key range over {world} GPUs "
+                               "(ps-lite rule), Pull/Push = NCCL all_to_all of the active rows"}),
+            "roofline": {"bound": "nvlink", "kernel": "all_to_all of active rows (pull + push)",
+                         "achieved": a2a_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": nvl, "unit": "GB/s",
+                         "frac": a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / nvl, "traffic": None,
+                         "algorithmic_bytes": int(a2a_bytes),
+                         "note": "bytes that must cross NVLink per GPU per direction per step / whole step time"},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(wall0, wall1), "loss_per_example": prog.loss / max(prog.nrows, 1),
+        }
+        print(json.dumps(line))
+    E.close()
+    dist.destroy_process_group()

@@ -177,10 +177,14 @@ int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset,
 int dfb_wait_step(dfb_handle h, dfb_progress* out);
 
 /* per-stage device timing with CUDA events on the handle's stream (bench.py's roofline):
- * stage 0 = key lookup + pull, 1 = FM forward/backward kernel, 2 = AUC, 3 = FTRL/AdaGrad update.
- * dfb_profile_read returns the accumulated milliseconds and launch counts and resets them. */
+ * stage 0 = key lookup + pull, 1 = FM forward kernel, 2 = AUC, 3 = CSC sort of the batch,
+ * 4 = per-key gradient reduce + FTRL/AdaGrad update (+ InitV pass).
+ * dfb_profile_read returns the accumulated milliseconds and launch counts of the DFB_NUM_STAGES
+ * stages and resets them.  While profiling, AUC runs on the main stream (otherwise it overlaps
+ * the update on an auxiliary stream). */
+#define DFB_NUM_STAGES 5
 int dfb_profile(dfb_handle h, int enable);
-int dfb_profile_read(dfb_handle h, double* stage_ms4, uint64_t* stage_count4);
+int dfb_profile_read(dfb_handle h, double* stage_ms, uint64_t* stage_count);
 
 /* ---------------------------------------------------------------------------------
  * model inspection (tests, checkpointing): read entries of the table.
@@ -203,11 +207,16 @@ uint32_t dfb_key_owner(uint64_t reversed_key, uint32_t num_shards);
 int dfb_shard_bounds(const uint64_t* sorted_keys, size_t n, uint32_t num_shards,
                      size_t* bounds_out);
 
-/* device-side building blocks for the sharded store (all pointers are device memory,
- * work is enqueued on the handle's stream; see difacto_b200/sharded.py for the protocol):
- *   owner side of Pull:  keys -> rows {w, has_V, V[ks]} packed for the all-to-all
- *   owner side of Push:  received {gw, gxxp, gV[ks]} rows applied with FTRL/AdaGrad
- *   worker side:         FM forward/backward on a pulled dense buffer               */
+/* device-side building blocks for the sharded store (all pointers are device memory, work is
+ * enqueued on the handle's stream; difacto_b200/sharded.py holds the protocol):
+ *   dfb_dev_feacnt     owner: Update(kFeaCount) for the keys one worker sent
+ *   dfb_dev_pull_rows  owner side of Pull: keys -> dense rows {w[n], has_V[n] (-1/1), V[n][ks]}
+ *                      packed for the all-to-all (SGDUpdater::Get, dense instead of ragged)
+ *   dfb_dev_fm_step    worker: Predict/Evaluate/penalty/AUC/CalcGrad on the pulled dense buffers;
+ *                      writes the COMPLETE gradient rows gw[n], gV[n][ks] (incl. the -V*XXp term
+ *                      computed with the pulled V, fm_loss.h:181-188) for the keys with has_V >= 0
+ *   dfb_dev_push_rows  owner side of Push(kGradient): FTRL/AdaGrad from the rows one worker sent;
+ *                      has_V is the worker's pull-time view (lens[i] > 1, sgd_updater.cc:91)   */
 int dfb_row_stride(dfb_handle h);  /* ks: V_dim rounded up to a multiple of 4 floats */
 int dfb_dev_feacnt(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_cnt);
 int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w_out,
@@ -215,9 +224,9 @@ int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w
 int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset,
                     const uint32_t* d_index, const float* d_value_or_null, const float* d_label,
                     size_t nkeys, const float* d_w, const int* d_hasv, const float* d_V,
-                    int is_train, float* d_gw_out, float* d_gxxp_out, float* d_gV_out);
+                    int is_train, float* d_gw_out, float* d_gV_out);
 int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_gw,
-                      const float* d_gxxp, const int* d_hasv, const float* d_gV);
+                      const int* d_hasv, const float* d_gV);
 /* the CUDA stream (cudaStream_t) the handle enqueues on, for event interop with torch */
 void* dfb_stream(dfb_handle h);
 
