@@ -174,9 +174,14 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
                       const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
                       const float* p_row, const float* pxv, int* flags, int accumulate_penalty,
                       cudaStream_t s);
-int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* col_start,
-                     const int* col_end, const void* occ_sorted, bool valued, const float* p_row,
-                     const float* pxv, float* gw_out, const float* V_pulled, float* gV_out,
+int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_pulled,
+                     const int* hasv, size_t n, const int* col_start, const int* col_end,
+                     const void* occ_sorted, bool valued, const float* p_row, const float* pxv,
+                     float* gw_out, const float* V_pulled, float* gV_out, int accumulate_penalty,
                      cudaStream_t s);
+// owner side of the sharded Push for V_dim in {8,16,32,64,128}: FTRL/AdaGrad from complete dense
+// gradient rows; returns -1 for other V_dim (use launch_update_dense)
+int launch_update_pushed(Table& t, const Params& p, const int* slot, const int* hasv, size_t n,
+                         const float* gw, const float* gV, int* flags, cudaStream_t s);
 
 }  // namespace dfb

@@ -1048,9 +1048,10 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_of
     h->launches += launch_csc_build(d_index, h->occ.p, d_value != nullptr, nnz, nkeys, h->lidx_sorted.as<uint32_t>(),
                                     h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
                                     h->cub.bytes, s);
-    int nl = launch_bwd_dense(k, ks, d_hasv, nkeys, h->col_start.as<int>(), h->col_end.as<int>(), h->occ_sorted.p,
-                              d_value != nullptr, h->p_row.as<float>(), h->pxv.as<float>(), d_gw_out, d_V, d_gV_out,
-                              s);
+    // the penalty of the pulled weights (sgd_learner.cc:148) is accumulated by the same kernel
+    int nl = launch_bwd_dense(h->prm, h->tab.prog, ks, d_w, d_hasv, nkeys, h->col_start.as<int>(),
+                              h->col_end.as<int>(), h->occ_sorted.p, d_value != nullptr, h->p_row.as<float>(),
+                              h->pxv.as<float>(), d_gw_out, d_V, d_gV_out, 1, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
     h->launches += nl;
   } else if (is_train && k > 0) {
@@ -1065,7 +1066,7 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_of
                               h->auc_v.as<float>(), h->auc_tmp.p, h->auc_tmp.bytes, &h->tab.prog->auc, s);
   }
   // the worker evaluates the penalty of what it pulled (sgd_learner.cc:148)
-  h->launches += launch_penalty(h->prm, h->tab.prog, d_w, d_hasv, d_V, ks, 1, nkeys, s);
+  if (!sorted) h->launches += launch_penalty(h->prm, h->tab.prog, d_w, d_hasv, d_V, ks, 1, nkeys, s);
   DFB_CUDA(h, cudaGetLastError());
   return DFB_OK;
 }
@@ -1078,8 +1079,12 @@ int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const floa
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
   h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
-  h->launches += launch_update_dense(h->tab, h->prm, h->slot.as<int>(), d_hasv, 1, n, d_gw, nullptr, d_gV,
-                                     h->flags.as<int>(), 0, 0, s);
+  int nl = h->force_generic ? -1 : launch_update_pushed(h->tab, h->prm, h->slot.as<int>(), d_hasv, n, d_gw, d_gV,
+                                                        h->flags.as<int>(), s);
+  if (nl < 0)
+    nl = launch_update_dense(h->tab, h->prm, h->slot.as<int>(), d_hasv, 1, n, d_gw, nullptr, d_gV,
+                             h->flags.as<int>(), 0, 0, s);
+  h->launches += nl;
   h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, h->flags.as<int>(), h->pos.as<int>(),
                               h->cub.p, h->cub.bytes, s);
   DFB_CUDA(h, cudaGetLastError());

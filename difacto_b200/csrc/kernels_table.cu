@@ -420,22 +420,36 @@ __global__ void k_pack_ragged(Table t, Params p, const int* __restrict__ slot, s
   }
 }
 
-__global__ void k_gather_rows(Table t, const int* __restrict__ slot, size_t n, float* __restrict__ w_out,
-                              int* __restrict__ hasv_out, float* __restrict__ V_out) {
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) k_gather_rows(Table t, const int* __restrict__ slot, size_t n,
+                                                     float* __restrict__ w_out, int* __restrict__ hasv_out,
+                                                     float* __restrict__ V_out) {
+  const int lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t i = warp0; i < n; i += nwarps) {
-    const int s = slot[i];
-    const int vr = s >= 0 ? t.tab[s].vrow : -1;
-    if (lane == 0) {
-      w_out[i] = s >= 0 ? t.tab[s].w : 0.f;
+  const int nv4 = t.ks / 4;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    int vr = -1;
+    if (i < n) {
+      const int s = slot[i];
+      float w = 0.f;
+      if (s >= 0) { w = t.tab[s].w; vr = t.tab[s].vrow; }
+      w_out[i] = w;
       hasv_out[i] = vr >= 0 ? 1 : -1;
     }
-    if (vr >= 0 && V_out) {
-      const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vr * t.rs);
-      float4* dst = reinterpret_cast<float4*>(V_out + i * (size_t)t.ks);
-      for (int l = lane; l < t.ks / 4; l += 32) dst[l] = src[l];
+    if (!V_out) continue;
+    // two rows per pass (16 lanes each), four passes in flight
+#pragma unroll 1
+    for (int pass = 0; pass < 16; pass += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int kk = (pass + q) * 2 + grp;
+        const int vr_k = __shfl_sync(kFull, vr, kk);
+        if (vr_k < 0) continue;
+        const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vr_k * t.rs);
+        float4* dst = reinterpret_cast<float4*>(V_out + (base + kk) * (size_t)t.ks);
+        for (int l = sub; l < nv4; l += 16) dst[l] = src[l];
+      }
     }
   }
 }
@@ -559,7 +573,9 @@ __device__ __forceinline__ void load_occ(const void* occ, int o, uint32_t& row, 
 // metadata loads, 32 independent entry sectors in flight, the scalar reductions and FTRL.
 // Phase B walks the 32 keys G at a time with LPR lanes (one float4 each) per 8K-byte table row,
 // UNRB row-groups in flight; the first occurrence's p*XV row is fetched together with V|cg.
-template <int K, bool HAS_VAL, bool APPLY>
+// SRC 0: gradient reduced from the occurrence lists (fused step / worker).  SRC 1: gradient read
+// from dense rows gw_in[n], gV_in[n][K] that a worker pushed (owner side of the sharded store).
+template <int K, bool HAS_VAL, bool APPLY, int SRC = 0>
 __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int* __restrict__ slot,
                                                     const int* __restrict__ pull_vrow, size_t n,
                                                     const int* __restrict__ col_start,
@@ -585,8 +601,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
     int s = -1, vr = -1, o0 = 0, o1 = 0;
     if (active) {
       vr = pull_vrow[i];
-      o0 = col_start[i];
-      o1 = col_end[i];
+      if (SRC == 0) { o0 = col_start[i]; o1 = col_end[i]; }
       if (APPLY) s = slot[i];
     }
     Entry* e = nullptr;
@@ -597,6 +612,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
     }
     float gw = 0.f, xxp = 0.f, x0 = 0.f;
     uint32_t row0 = 0;
+    if (SRC == 1 && active) gw = p_row[i];      // dense source: p_row aliases gw_in
     for (int o = o0; o < o1; ++o) {
       uint32_t row; float x;
       load_occ<HAS_VAL>(occ, o, row, x);
@@ -606,8 +622,10 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
       if (o == o0) { row0 = row; x0 = x; }
     }
     if (!HAS_VAL) xxp = gw;
+    if (SRC == 1) xxp = 0.f;                    // pushed rows are complete gradients
     if (APPLY) {
       if (s >= 0) {
+        if (vr >= 0) vr = SRC == 1 ? e->vrow : vr;   // SRC 1: pull_vrow is the worker's has_V flag
         if (acc_pen) pen += pen_w(p, sc.y);
         const bool became_nz = ftrl_step(p, gw, sc.y, sc.z, sc.w);
         *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
@@ -618,6 +636,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
       if (s < 0) vr = -1;
     } else if (active) {
       gw_out[i] = gw;
+      if (acc_pen) pen += pen_w(p, slot ? __int_as_float(slot[i]) : 0.f);   // worker: slot aliases the pulled w
     }
     // ---------------- phase B: the table rows, G keys per pass ----------------
 #pragma unroll 1
@@ -645,7 +664,10 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
             const size_t ik = base + (size_t)((pass + q) * G + grp);
             v[q] = __ldg(reinterpret_cast<const float4*>(V_pulled + ik * (size_t)K + sub * 4));
           }
-          if (o1k[q] > o0k[q]) {
+          if (SRC == 1) {
+            const size_t ik = base + (size_t)((pass + q) * G + grp);
+            g[q] = __ldg(reinterpret_cast<const float4*>(pxv + ik * (size_t)K + sub * 4));   // pxv aliases gV_in
+          } else if (o1k[q] > o0k[q]) {
             const float4 tt = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)r0 * K + sub * 4));
             g[q] = make_float4(__fmul_rn(tt.x, xx0), __fmul_rn(tt.y, xx0), __fmul_rn(tt.z, xx0),
                                __fmul_rn(tt.w, xx0));                                   // spmm.h:152-154
@@ -675,6 +697,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
         } else {
           const size_t ik = base + (size_t)((pass + q) * G + grp);
           const float xp = xxpk[q];
+          if (acc_pen) pen += 0.5f * p.V_l2 * (v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w);
           *reinterpret_cast<float4*>(gV_out + ik * (size_t)K + sub * 4) =
               make_float4(__fsub_rn(g[q].x, __fmul_rn(v[q].x, xp)), __fsub_rn(g[q].y, __fmul_rn(v[q].y, xp)),
                           __fsub_rn(g[q].z, __fmul_rn(v[q].z, xp)), __fsub_rn(g[q].w, __fmul_rn(v[q].w, xp)));
@@ -682,7 +705,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
       }
     }
   }
-  if (APPLY && acc_pen) {
+  if (acc_pen) {
     pen = warp_sum(pen);
     if (lane == 0 && pen != 0.f) atomicAdd(&t.prog->penalty, (double)pen);
   }
@@ -769,7 +792,7 @@ int launch_pack_ragged(Table& t, const Params& p, const int* slot, size_t n, int
 int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* hasv_out, float* V_out,
                        cudaStream_t s) {
   if (n == 0) return 0;
-  k_gather_rows<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(t, slot, n, w_out, hasv_out, V_out);
+  k_gather_rows<<<grid_warps((n + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, slot, n, w_out, hasv_out, V_out);
   return 1;
 }
 
@@ -888,24 +911,24 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
   return -1;
 }
 
-int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* col_start, const int* col_end,
-                     const void* occ_sorted, bool valued, const float* p_row, const float* pxv, float* gw_out,
-                     const float* V_pulled, float* gV_out, cudaStream_t s) {
+int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_pulled, const int* hasv, size_t n,
+                     const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
+                     const float* p_row, const float* pxv, float* gw_out, const float* V_pulled, float* gV_out,
+                     int acc_pen, cudaStream_t s) {
   if (n == 0) return 0;
-  if (ks != V_dim) return -1;
+  if (ks != p.V_dim) return -1;
   Table t;
-  Params p;
-  memset(&p, 0, sizeof(p));
-  p.V_dim = V_dim;
+  t.prog = prog;
+  const int* w_alias = reinterpret_cast<const int*>(w_pulled);
 #define DFB_BD(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
-    if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, nullptr, hasv, n, col_start, col_end, \
-                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, V_pulled, gV_out);                           \
-    else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, nullptr, hasv, n, col_start, col_end,      \
-                   occ_sorted, p_row, pxv, nullptr, 0, gw_out, V_pulled, gV_out);                           \
+    if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, col_start, col_end, \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out);                     \
+    else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, col_start, col_end,      \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out);                     \
   } while (0)
-  switch (V_dim) {
+  switch (p.V_dim) {
     case 8: DFB_BD(8); return 1;
     case 16: DFB_BD(16); return 1;
     case 32: DFB_BD(32); return 1;
@@ -913,6 +936,28 @@ int launch_bwd_dense(int V_dim, int ks, const int* hasv, size_t n, const int* co
     case 128: DFB_BD(128); return 1;
   }
 #undef DFB_BD
+  return -1;
+}
+
+// owner side of Push(kGradient) for the specialised V_dims: same phase A/B kernel, gradient read
+// from the dense rows a worker sent
+int launch_update_pushed(Table& t, const Params& p, const int* slot, const int* hasv, size_t n, const float* gw,
+                         const float* gV, int* flags, cudaStream_t s) {
+  if (n == 0) return 0;
+#define DFB_UP(K)                                                                                          \
+  do {                                                                                                     \
+    const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
+    k_bwd_update<K, false, true, 1><<<grid, 256, 0, s>>>(t, p, slot, hasv, n, nullptr, nullptr, nullptr, gw, \
+                                                          gV, flags, 0, nullptr, nullptr, nullptr);         \
+  } while (0)
+  switch (p.V_dim) {
+    case 8: DFB_UP(8); return 1;
+    case 16: DFB_UP(16); return 1;
+    case 32: DFB_UP(32); return 1;
+    case 64: DFB_UP(64); return 1;
+    case 128: DFB_UP(128); return 1;
+  }
+#undef DFB_UP
   return -1;
 }
 

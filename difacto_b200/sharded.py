@@ -89,7 +89,29 @@ class ShardedStore:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.ks = backend.ks
         self._buf = {}
-        self.timers = None
+        self.timers = None      # set to {} to collect per-phase CUDA-event timings (device tensors only)
+        self._marks = []
+
+    def _mark(self, name):
+        if self.timers is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._marks.append((name, ev))
+
+    def flush_timers(self):
+        """fold the recorded marks into self.timers[name] = [total_ms, count] (synchronises)"""
+        if self.timers is None or not self._marks:
+            return self.timers
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(self._marks[:-1], self._marks[1:]):
+            if n1 == "begin":
+                continue
+            t = self.timers.setdefault(n1, [0.0, 0])
+            t[0] += e0.elapsed_time(e1)
+            t[1] += 1
+        self._marks = []
+        return self.timers
 
     def _get(self, name, n, shape_tail, dtype):
         t = self._buf.get(name)
@@ -111,6 +133,7 @@ class ShardedStore:
 
         batch: dict(nrows, nnz, U, off, lidx, val|None, lab, keys, cnt|None, bounds[S+1])"""
         S, U, ks = self.S, batch["U"], self.ks
+        self._mark("begin")
         bounds = batch["bounds"]
         send = [int(bounds[i + 1] - bounds[i]) for i in range(S)]
         if S == 1:
@@ -124,6 +147,7 @@ class ShardedStore:
         seg = np.concatenate([[0], np.cumsum(recv)]).astype(np.int64)
         keys_r = self._get("keys_r", R, (), torch.int64)
         self._a2a(keys_r, batch["keys"], recv, send)
+        self._mark("a2a_counts_keys")
         if push_cnt:
             cnt_r = self._get("cnt_r", R, (), torch.float32)
             self._a2a(cnt_r, batch["cnt"], recv, send)
@@ -135,6 +159,7 @@ class ShardedStore:
         hasv_r = self._get("hasv_r", R, (), torch.int32)
         V_r = self._get("V_r", R, (ks,), torch.float32)
         self.b.pull_rows(keys_r, w_r, hasv_r, V_r)
+        self._mark("owner_gather")
         w = self._get("w", U, (), torch.float32)
         hasv = self._get("hasv", U, (), torch.int32)
         V = self._get("V", U, (ks,), torch.float32)
@@ -142,10 +167,12 @@ class ShardedStore:
         self._a2a(hasv, hasv_r, send, recv)
         if ks:
             self._a2a(V, V_r, send, recv)
+        self._mark("a2a_pull")
         # ---- Predict / Evaluate / CalcGrad ----
         gw = self._get("gw", U, (), torch.float32)
         gV = self._get("gV", U, (ks,), torch.float32)
         self.b.fm_step(batch, w, hasv, V, is_train, gw, gV)
+        self._mark("worker_fm")
         if not is_train:
             return
         # ---- Push(kGradient) ----
@@ -154,9 +181,11 @@ class ShardedStore:
         self._a2a(gw_r, gw, recv, send)
         if ks:
             self._a2a(gV_r, gV, recv, send)
+        self._mark("a2a_push")
         for src in range(S):        # one Update(kGradient) per worker, rank order
             a, b = int(seg[src]), int(seg[src + 1])
             self.b.push_rows(keys_r[a:b], gw_r[a:b], hasv_r[a:b], gV_r[a:b])
+        self._mark("owner_update")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -233,6 +262,14 @@ def bench_main(args, rank, world, local_rank, benchmod):
         launches = E.launch_count() - launches0
         prog = E.read_progress()
 
+        # ---- per-phase CUDA-event timings (separate region) ----
+        store.timers = {}
+        for t in range(max(4, args.steps // 2)):
+            store.step(devb[(args.warmup + t) % nb], True)
+        phases = {k2: v2[0] / max(v2[1], 1) for k2, v2 in store.flush_timers().items()}
+        store.timers = None
+        E.read_progress()
+
         # ---- e2e: per-step H2D of the localized batch from pinned memory + Progress read back ----
         e2e = None
         if not args.no_e2e:
@@ -276,7 +313,16 @@ def bench_main(args, rank, world, local_rank, benchmod):
                          "note": "bytes that must cross NVLink per GPU per direction per step / whole step time"},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(wall0, wall1), "loss_per_example": prog.loss / max(prog.nrows, 1),
+            "phases_ms_per_step_rank0": phases,
         }
-        print(json.dumps(line))
-    E.close()
+        print(json.dumps(line), flush=True)
+    # Tensors (device and pinned host) that were used on the engine's stream record events on it
+    # when they are freed, which at interpreter teardown can happen after the stream is gone:
+    # finish cleanly and leave without running destructors.
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
+    import sys
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
