@@ -1,0 +1,185 @@
+// difacto_b200/host/src/sgd_learner.cc -- see sgd_learner.h.  Control flow follows
+// src/sgd/sgd_learner.cc of the reference (cited per function); the arithmetic lives on the GPU.
+#include "difacto_b200/sgd_learner.h"
+
+#include <cstdio>
+
+namespace difacto {
+
+Loss* Loss::Create(const std::string& type, int nthreads) {   // src/loss/loss.cc:13-26
+  if (type != "fm") throw Error("unknown loss type: " + type + " (the B200 engine provides \"fm\")");
+  Loss* l = new GpuFMLoss();
+  l->set_nthreads(nthreads);
+  return l;
+}
+
+Store* Store::Create() { return new GpuStore(); }   // src/store/store.cc:8-15
+
+Learner* Learner::Create(const std::string& type) {   // src/learner.cc:15-26
+  if (type == "sgd") return new SGDLearner();
+  throw Error("unknown learner type: " + type + " (the B200 engine accelerates the sgd learner)");
+}
+
+// SGDLearner::Init, sgd_learner.cc:229-246
+KWArgs SGDLearner::Init(const KWArgs& kwargs) {
+  KWArgs remain = param_.InitAllowUnknown(kwargs);
+  auto* updater = new GpuSGDUpdater();
+  std::shared_ptr<Updater> holder(updater);
+  remain = updater->Init(remain);
+  remain.push_back(std::make_pair("V_dim", std::to_string(updater->param().V_dim)));   // :236
+  store_ = Store::Create();
+  store_->SetUpdater(holder);
+  remain = store_->Init(remain);
+  loss_ = Loss::Create(param_.loss, 2);
+  static_cast<GpuFMLoss*>(loss_)->AttachEngine(updater->engine());
+  remain = loss_->Init(remain);
+  return remain;
+}
+
+// SGDLearner::RunScheduler, sgd_learner.cc:31-68
+void SGDLearner::RunScheduler() {
+  real_t pre_loss = 0, pre_val_auc = 0;
+  for (int k = 0; k < param_.max_num_epochs; ++k) {
+    sgd::Progress train_prog, val_prog;
+    if (verbose) printf("Start epoch %d\n", k);
+    RunEpoch(k, sgd::Job::kTraining, &train_prog);
+    if (verbose) printf(" - Training: %s\n", train_prog.TextString().c_str());
+    if (!param_.data_val.empty()) {
+      RunEpoch(k, sgd::Job::kValidation, &val_prog);
+      if (verbose) printf(" - Validation: %s\n", val_prog.TextString().c_str());
+    }
+    for (const auto& cb : epoch_end_callback_) cb(k, train_prog, val_prog);
+    real_t eps = std::fabs(train_prog.loss - pre_loss) / pre_loss;
+    if (eps < param_.stop_rel_objv) {
+      if (verbose) printf("Change of loss [%g] < stop_rel_objv [%g]\n", eps, param_.stop_rel_objv);
+      break;
+    }
+    if (val_prog.auc > 0) {
+      eps = (val_prog.auc - pre_val_auc) / val_prog.nrows;
+      if (eps < param_.stop_val_auc) {
+        if (verbose) printf("Change of validation AUC [%g] < stop_val_auc [%g]\n", eps, param_.stop_val_auc);
+        break;
+      }
+    }
+    if (k + 1 >= param_.max_num_epochs && verbose) printf("Reach maximal number of epochs\n");
+    pre_loss = train_prog.loss;
+    pre_val_auc = val_prog.auc;
+    if (verbose) fflush(stdout);
+  }
+}
+
+// SGDLearner::RunEpoch, sgd_learner.cc:70-111: n = NumWorkers * num_jobs_per_epoch file parts,
+// executed in order (the reference's LocalTracker runs them serially on one thread too)
+void SGDLearner::RunEpoch(int epoch, int job_type, sgd::Progress* prog) {
+  const int n = store_->NumWorkers() * param_.num_jobs_per_epoch;
+  for (int i = 0; i < n; ++i) {
+    sgd::Job job;
+    job.type = job_type; job.epoch = epoch; job.num_parts = n; job.part_idx = i;
+    sgd::Progress p;
+    IterateData(job, &p);
+    prog->Merge(p);
+  }
+}
+
+// SGDLearner::GetPos, sgd_learner.cc:113-127
+void SGDLearner::GetPos(const SArray<int>& len, SArray<int>* w_pos, SArray<int>* V_pos) {
+  const size_t n = len.size();
+  w_pos->resize(n);
+  V_pos->resize(n);
+  int p = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const int l = len[i];
+    (*w_pos)[i] = l == 0 ? -1 : p;
+    (*V_pos)[i] = l > 1 ? p + 1 : -1;
+    p += l;
+  }
+}
+
+// SGDLearner::EvaluatePenalty, sgd_learner.cc:249-273
+real_t SGDLearner::EvaluatePenalty(const SArray<real_t>& weights, const SArray<int>& w_pos,
+                                   const SArray<int>& V_pos) {
+  const auto& param = GetUpdater()->param();
+  real_t objv = 0;
+  if (w_pos.size()) {
+    for (int p : w_pos) {
+      if (p == -1) continue;
+      const real_t w = weights[p];
+      objv += param.l1 * std::fabs(w) + .5 * param.l2 * w * w;
+    }
+    for (int p : V_pos) {
+      if (p == -1) continue;
+      for (int i = 0; i < param.V_dim; ++i) {
+        const real_t V = weights[p + i];
+        objv += .5 * param.V_l2 * V * V;
+      }
+    }
+  } else {
+    for (real_t w : weights) objv += param.l1 * std::fabs(w) + .5 * param.l2 * w * w;
+  }
+  return objv;
+}
+
+// the pull_callback of IterateData (sgd_learner.cc:138-177) as ONE fused device step
+void SGDLearner::BatchFused(const RowBlockContainer<unsigned>& data, const std::vector<feaid_t>& keys,
+                            const std::vector<real_t>* cnt, bool train, sgd::Progress* prog) {
+  const auto& eng = GetUpdater()->engine();
+  dfb_progress pr;
+  eng->Check(dfb_train_step(eng->handle(), data.Size(), reinterpret_cast<const uint64_t*>(data.offset.data()),
+                            data.index.data(), data.value.empty() ? nullptr : data.value.data(), data.label.data(),
+                            keys.data(), keys.size(), cnt ? cnt->data() : nullptr, train ? 1 : 0, &pr, nullptr),
+             "dfb_train_step");
+  prog->loss += pr.loss; prog->penalty += pr.penalty; prog->auc += pr.auc; prog->nrows += pr.nrows;
+}
+
+// the same minibatch through the reference's own plugin calls (sgd_learner.cc:138-177, :214-217)
+void SGDLearner::BatchPluginCalls(const RowBlockContainer<unsigned>& data_c, const std::vector<feaid_t>& keys,
+                                  const std::vector<real_t>* cnt, bool train, sgd::Progress* prog) {
+  SArray<feaid_t> feaids(const_cast<feaid_t*>(keys.data()), keys.size());
+  if (cnt) {
+    SArray<real_t> feacnt(const_cast<real_t*>(cnt->data()), cnt->size());
+    store_->Wait(store_->Push(feaids, Store::kFeaCount, feacnt, SArray<int>()));
+  }
+  SArray<real_t> values;
+  SArray<int> lengths;
+  store_->Pull(feaids, Store::kWeight, &values, &lengths);
+  auto data = data_c.GetBlock();
+  prog->nrows += data.size;
+  SArray<real_t> pred(data.size);
+  SArray<int> w_pos, V_pos;
+  GetPos(lengths, &w_pos, &V_pos);
+  std::vector<SArray<char>> inputs = {SArray<char>(values), SArray<char>(w_pos), SArray<char>(V_pos)};
+  loss_->Predict(data, inputs, &pred);
+  prog->loss += loss_->Evaluate(data.label, pred);
+  prog->penalty += EvaluatePenalty(values, w_pos, V_pos);
+  prog->auc += static_cast<GpuFMLoss*>(loss_)->AUC(data.label, pred);
+  if (train) {
+    SArray<real_t> grads(values.size());
+    inputs.push_back(SArray<char>(pred));
+    loss_->CalcGrad(data, inputs, &grads);
+    store_->Push(feaids, Store::kGradient, grads, lengths);
+  }
+}
+
+// SGDLearner::IterateData, sgd_learner.cc:129-227
+void SGDLearner::IterateData(const sgd::Job& job, sgd::Progress* progress) {
+  const bool train = job.type == sgd::Job::kTraining;
+  // training: BatchReader(batch_size, shuffle window = batch_size*shuffle, neg_sampling) (:182-188);
+  // validation: plain reader, here in chunks of 65536 rows (:190-194 reads 256 MB chunks)
+  BatchReader reader(train ? param_.data_in : param_.data_val, param_.data_format,
+                     static_cast<unsigned>(job.part_idx), static_cast<unsigned>(job.num_parts),
+                     train ? static_cast<unsigned>(param_.batch_size) : 65536u,
+                     train ? static_cast<unsigned>(param_.batch_size) * static_cast<unsigned>(param_.shuffle) : 0u,
+                     train ? param_.neg_sampling : 1.0f);
+  while (reader.Next()) {
+    RowBlockContainer<unsigned> data;
+    std::vector<feaid_t> feaids;
+    std::vector<real_t> feacnt;
+    const bool push_cnt = train && job.epoch == 0;   // :201-202
+    Localizer lc(-1, 2);
+    lc.Compact(reader.Value(), &data, &feaids, push_cnt ? &feacnt : nullptr);
+    if (param_.fused) BatchFused(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
+    else BatchPluginCalls(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
+  }
+}
+
+}  // namespace difacto
