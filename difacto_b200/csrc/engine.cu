@@ -38,6 +38,7 @@ struct dfb_engine {
   int compute_auc = 1;
   int force_generic = 0;
   int scatter_sorted = 1;   // 1: atomic-free sorted reduction (deterministic); 0: red.global atomics
+  int overlap_auc = 1;      // run the AUC kernels on the auxiliary stream, concurrently with the update
   cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
   cudaEvent_t ev_fm_done = nullptr, ev_auc_done = nullptr;
   Table tab;
@@ -326,15 +327,16 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
     DFB_TRY(h->ensure(h->auc_k, nrows * sizeof(float)));
     DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
     DFB_TRY(h->ensure(h->auc_tmp, sort_tmp_bytes(nrows)));
-    cudaStream_t as = h->profile ? s : h->aux_stream;
-    if (!h->profile) {
+    const bool side = h->overlap_auc && !h->profile;
+    cudaStream_t as = side ? h->aux_stream : s;
+    if (side) {
       DFB_CUDA(h, cudaEventRecord(h->ev_fm_done, s));
       DFB_CUDA(h, cudaStreamWaitEvent(as, h->ev_fm_done, 0));
     }
     StageTimer tm(h, 2);
     h->launches += launch_auc(d_lab, h->pred.as<float>(), nrows, nullptr, nullptr, h->auc_k.as<float>(),
                               h->auc_v.as<float>(), h->auc_tmp.p, h->auc_tmp.bytes, &h->tab.prog->auc, as);
-    if (!h->profile) {
+    if (side) {
       DFB_CUDA(h, cudaEventRecord(h->ev_auc_done, as));
       auc_pending = true;
     }
@@ -439,6 +441,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     else if (k == "V_capacity") { if (!need_int(0, 1LL << 30)) { delete h; return DFB_ERR_PARAM; } v_capacity = x; }
     else if (k == "compute_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->compute_auc = (int)x; }
     else if (k == "force_generic") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->force_generic = (int)x; }
+    else if (k == "overlap_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->overlap_auc = (int)x; }
     else if (k == "scatter") {
       if (v == "sorted") h->scatter_sorted = 1;
       else if (v == "atomic") h->scatter_sorted = 0;

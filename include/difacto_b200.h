@@ -72,6 +72,7 @@ typedef struct {
  *                         the batch, fused with the FTRL/AdaGrad step (no atomics, bit-reproducible,
  *                         row order per key like SpMM::TransTimes); atomic = fp32 red.global scatter
  *                         into dense gradient rows followed by a separate update kernel
+ *   overlap_auc (1)       run the AUC kernels on an auxiliary stream, overlapped with the update
  *   force_generic (0)     1 = use the any-V_dim kernels even where a specialised one exists (tests)
  * Keys that are neither are returned through dfb_unknown_kwarg, mirroring the
  * "return the unconsumed kwargs" convention (updater.h:34, main.cc:25-31).
