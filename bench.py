@@ -380,10 +380,19 @@ def main_b200(args, rank, world, local_rank):
     fwd = stages_fwd["fm"]
     fwd_ms = fwd["ms"] / max(fwd["count"], 1)
     ach_fwd = bytes_fwd / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+    traffic = None
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of the same kernel/config
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        if args.batch == 65536 and nnz == 100 and args.workload == "synthetic":
+            e_ = tr.get(f"k_bwd_update<{k}>")
+            if e_:
+                traffic = e_["dram_read_bytes"] + e_["dram_write_bytes"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm",
                 "kernel": f"k_bwd_update<{k}> (per-key gradient reduce fused with FTRL/AdaGrad; dominant kernel of the step; "
                           "the timed stage also contains the 3 tiny InitV-pass kernels)",
-                "achieved": ach_upd, "peak": peak, "unit": "GB/s", "frac": ach_upd / peak, "traffic": None,
+                "achieved": ach_upd, "peak": peak, "unit": "GB/s", "frac": ach_upd / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": upd_ms, "algorithmic_bytes": int(bytes_upd),
                 "gather_interaction": {"kernel": f"k_fm_fast<{k},predict> (gather+interaction, K1 of SURVEY 8d; validation launches)",
                                        "achieved": ach_fwd, "frac": ach_fwd / peak, "kernel_ms": fwd_ms,
