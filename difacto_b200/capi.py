@@ -32,6 +32,8 @@ EXPORTS = [
     "dfb_read_entries", "dfb_rng_state", "dfb_key_owner", "dfb_shard_bounds", "dfb_row_stride",
     "dfb_dev_feacnt", "dfb_dev_pull_rows", "dfb_dev_fm_step", "dfb_dev_push_rows", "dfb_stream",
     "dfb_wait_step", "dfb_profile", "dfb_profile_read",
+    "dfb_peer_alloc", "dfb_peer_open", "dfb_peer_close", "dfb_peer_free", "dfb_dev_pull_rows_peer",
+    "dfb_dev_fm_step_peer",
 ]
 
 _LIB = None
@@ -81,6 +83,12 @@ def lib():
         L.dfb_wait_step.argtypes = [vp, C.POINTER(Progress)]
         L.dfb_profile.argtypes = [vp, C.c_int]
         L.dfb_profile_read.argtypes = [vp, vp, vp]
+        L.dfb_peer_alloc.argtypes = [vp, sz, C.POINTER(vp), vp]
+        L.dfb_peer_open.argtypes = [vp, vp, C.POINTER(vp)]
+        L.dfb_peer_close.argtypes = [vp, vp]
+        L.dfb_peer_free.argtypes = [vp, vp]
+        L.dfb_dev_pull_rows_peer.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+        L.dfb_dev_fm_step_peer.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp, vp]
         L.dfb_stream.restype = vp
         L.dfb_stream.argtypes = [vp]
         _LIB = L
@@ -296,6 +304,32 @@ class Engine:
     def dev_fm_step(self, nrows, nnz, d_off, d_idx, d_val, d_lab, nkeys, d_w, d_hasv, d_V, is_train, d_gw, d_gV):
         self._ck(self.L.dfb_dev_fm_step(self.h, nrows, nnz, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys,
                                         _p(d_w), _p(d_hasv), _p(d_V), int(is_train), _p(d_gw), _p(d_gV)))
+
+    # ---- NVLink peer stores (CUDA IPC) ----
+    def peer_alloc(self, nbytes):
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._ck(self.L.dfb_peer_alloc(self.h, nbytes, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def peer_open(self, handle):
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._ck(self.L.dfb_peer_open(self.h, buf, C.byref(ptr)))
+        return ptr.value
+
+    def dev_pull_rows_peer(self, d_keys, n, peer_w, peer_hasv, peer_V, d_hasv_local):
+        self._ck(self.L.dfb_dev_pull_rows_peer(self.h, _p(d_keys), n, _p(peer_w), _p(peer_hasv), _p(peer_V),
+                                               _p(d_hasv_local)))
+
+    def dev_fm_step_peer(self, nrows, nnz, d_off, d_idx, d_val, d_lab, nkeys, d_w, d_hasv, d_V, seg_bounds, peer_gw,
+                         peer_gV):
+        nseg = len(peer_gw)
+        sb = (C.c_size_t * (nseg + 1))(*[int(x) for x in seg_bounds])
+        gw = (C.c_void_p * nseg)(*[int(x) for x in peer_gw])
+        gV = (C.c_void_p * nseg)(*[int(x) for x in peer_gV])
+        self._ck(self.L.dfb_dev_fm_step_peer(self.h, nrows, nnz, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys,
+                                             _p(d_w), _p(d_hasv), _p(d_V), nseg, sb, gw, gV))
 
     def dev_push_rows(self, d_keys, n, d_gw, d_hasv, d_gV):
         self._ck(self.L.dfb_dev_push_rows(self.h, _p(d_keys), n, _p(d_gw), _p(d_hasv), _p(d_gV)))

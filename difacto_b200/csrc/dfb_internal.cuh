@@ -80,6 +80,15 @@ struct FmView {
   float* gxxp;
 };
 
+// where the worker's gradient rows go: locally contiguous (nseg == 0) or, per owner segment of the
+// sorted key list, straight into that owner's receive buffer over NVLink (peer pointers)
+struct SegDst {
+  int nseg;
+  int bounds[9];      // key index boundaries of the segments (nseg + 1 used)
+  float* gw[8];       // per segment: destination of gw for the segment's first key
+  float* gV[8];       // per segment: destination row of gV for the segment's first key
+};
+
 struct FmBatch {
   size_t nrows;
   const uint64_t* offset;   // size_t offsets, as in dmlc::RowBlock (dmlc/data.h:141)
@@ -132,7 +141,7 @@ int launch_pack_ragged(Table& t, const Params& p, const int* slot, size_t n, int
                        cudaStream_t s);
 // dense rows for the sharded store: w[n], hasv[n] (-1/1), V[n][ks]
 int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* hasv_out,
-                       float* V_out, cudaStream_t s);
+                       int* hasv_out2, float* V_out, cudaStream_t s);
 // FTRL/AdaGrad from per-key dense gradient rows (fused path and sharded push).
 //   pull_vrow[i] >= 0 <=> the worker saw a V row at pull time (lens[i] > 1); when
 //   vrow_is_flag the actual row is taken from the entry.
@@ -178,7 +187,7 @@ int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_
                      const int* hasv, size_t n, const int* col_start, const int* col_end,
                      const void* occ_sorted, bool valued, const float* p_row, const float* pxv,
                      float* gw_out, const float* V_pulled, float* gV_out, int accumulate_penalty,
-                     cudaStream_t s);
+                     const SegDst* seg, cudaStream_t s);
 // owner side of the sharded Push for V_dim in {8,16,32,64,128}: FTRL/AdaGrad from complete dense
 // gradient rows; returns -1 for other V_dim (use launch_update_dense)
 int launch_update_pushed(Table& t, const Params& p, const int* slot, const int* hasv, size_t n,

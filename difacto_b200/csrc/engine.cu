@@ -989,23 +989,102 @@ int dfb_dev_feacnt(dfb_handle h, const uint64_t* d_keys, size_t n, const float* 
   return DFB_OK;
 }
 
-int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w_out, int* d_hasv_out,
-                      float* d_V_out) {
+static int dev_pull_rows_impl(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w_out, int* d_hasv_out,
+                              int* d_hasv_out2, float* d_V_out) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
   h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
-  h->launches += launch_gather_rows(h->tab, h->slot.as<int>(), n, d_w_out, d_hasv_out,
+  h->launches += launch_gather_rows(h->tab, h->slot.as<int>(), n, d_w_out, d_hasv_out, d_hasv_out2,
                                     h->prm.V_dim > 0 ? d_V_out : nullptr, s);
   DFB_CUDA(h, cudaGetLastError());
   return DFB_OK;
 }
 
+int dfb_dev_pull_rows(dfb_handle h, const uint64_t* d_keys, size_t n, float* d_w_out, int* d_hasv_out,
+                      float* d_V_out) {
+  return dev_pull_rows_impl(h, d_keys, n, d_w_out, d_hasv_out, nullptr, d_V_out);
+}
+
+int dfb_dev_pull_rows_peer(dfb_handle h, const uint64_t* d_keys, size_t n, float* peer_w_out, int* peer_hasv_out,
+                           float* peer_V_out, int* d_hasv_local_out) {
+  return dev_pull_rows_impl(h, d_keys, n, peer_w_out, peer_hasv_out, d_hasv_local_out, peer_V_out);
+}
+
+// ---- peer-accessible buffers (CUDA IPC) for the NVLink store ----
+int dfb_peer_alloc(dfb_handle h, size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!h || !ptr || !handle64) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DFB_CUDA(h, cudaMalloc(ptr, bytes ? bytes : 256));
+  cudaIpcMemHandle_t mh;
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaError_t e = cudaIpcGetMemHandle(&mh, *ptr);
+  if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return h->cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle64, &mh, 64);
+  return DFB_OK;
+}
+
+int dfb_peer_open(dfb_handle h, const unsigned char* handle64, void** ptr) {
+  if (!h || !ptr || !handle64) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  DFB_CUDA(h, cudaIpcOpenMemHandle(ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+  return DFB_OK;
+}
+
+int dfb_peer_close(dfb_handle h, void* ptr) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DFB_CUDA(h, cudaIpcCloseMemHandle(ptr));
+  return DFB_OK;
+}
+
+int dfb_peer_free(dfb_handle h, void* ptr) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DFB_CUDA(h, cudaFree(ptr));
+  return DFB_OK;
+}
+
+static int dev_fm_step_impl(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
+                           const float* d_value, const float* d_label, size_t nkeys, const float* d_w,
+                           const int* d_hasv, const float* d_V, int is_train, float* d_gw_out, float* d_gV_out,
+                           const SegDst* seg);
+
 int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
                     const float* d_value, const float* d_label, size_t nkeys, const float* d_w, const int* d_hasv,
                     const float* d_V, int is_train, float* d_gw_out, float* d_gV_out) {
+  return dev_fm_step_impl(h, nrows, nnz, d_offset, d_index, d_value, d_label, nkeys, d_w, d_hasv, d_V, is_train,
+                          d_gw_out, d_gV_out, nullptr);
+}
+
+int dfb_dev_fm_step_peer(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
+                         const float* d_value, const float* d_label, size_t nkeys, const float* d_w,
+                         const int* d_hasv, const float* d_V, int nseg, const size_t* seg_bounds,
+                         float* const* peer_gw, float* const* peer_gV) {
+  if (!h) return DFB_ERR_INVALID;
+  if (nseg < 1 || nseg > 8 || !seg_bounds || !peer_gw || !peer_gV)
+    return h->fail(DFB_ERR_INVALID, "dfb_dev_fm_step_peer: 1..8 segments with destinations required");
+  SegDst sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.nseg = nseg;
+  for (int i = 0; i <= nseg; ++i) sd.bounds[i] = (int)seg_bounds[i];
+  for (int i = 0; i < nseg; ++i) { sd.gw[i] = peer_gw[i]; sd.gV[i] = peer_gV[i]; }
+  if ((size_t)sd.bounds[nseg] != nkeys) return h->fail(DFB_ERR_INVALID, "seg_bounds[nseg] must equal nkeys");
+  const int k = h->prm.V_dim;
+  if (!(h->scatter_sorted && !h->force_generic && fm_fast_supported(k) && h->tab.ks == k))
+    return h->fail(DFB_ERR_INVALID, "peer gradient stores need the sorted scatter path (V_dim in {8,16,32,64,128})");
+  return dev_fm_step_impl(h, nrows, nnz, d_offset, d_index, d_value, d_label, nkeys, d_w, d_hasv, d_V, 1,
+                          peer_gw[0], peer_gV[0], &sd);
+}
+
+static int dev_fm_step_impl(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
+                           const float* d_value, const float* d_label, size_t nkeys, const float* d_w,
+                           const int* d_hasv, const float* d_V, int is_train, float* d_gw_out, float* d_gV_out,
+                           const SegDst* seg) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
@@ -1054,7 +1133,7 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_of
     // the penalty of the pulled weights (sgd_learner.cc:148) is accumulated by the same kernel
     int nl = launch_bwd_dense(h->prm, h->tab.prog, ks, d_w, d_hasv, nkeys, h->col_start.as<int>(),
                               h->col_end.as<int>(), h->occ_sorted.p, d_value != nullptr, h->p_row.as<float>(),
-                              h->pxv.as<float>(), d_gw_out, d_V, d_gV_out, 1, s);
+                              h->pxv.as<float>(), d_gw_out, d_V, d_gV_out, 1, seg, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
     h->launches += nl;
   } else if (is_train && k > 0) {

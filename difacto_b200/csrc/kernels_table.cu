@@ -422,7 +422,7 @@ __global__ void k_pack_ragged(Table t, Params p, const int* __restrict__ slot, s
 
 __global__ void __launch_bounds__(256) k_gather_rows(Table t, const int* __restrict__ slot, size_t n,
                                                      float* __restrict__ w_out, int* __restrict__ hasv_out,
-                                                     float* __restrict__ V_out) {
+                                                     int* __restrict__ hasv_out2, float* __restrict__ V_out) {
   const int lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(Table t, const int* __restr
       if (s >= 0) { w = t.tab[s].w; vr = t.tab[s].vrow; }
       w_out[i] = w;
       hasv_out[i] = vr >= 0 ? 1 : -1;
+      if (hasv_out2) hasv_out2[i] = vr >= 0 ? 1 : -1;
     }
     if (!V_out) continue;
     // two rows per pass (16 lanes each), four passes in flight
@@ -585,7 +586,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
                                                     const float* __restrict__ pxv, int* __restrict__ flags,
                                                     int acc_pen, float* __restrict__ gw_out,
                                                     const float* __restrict__ V_pulled,
-                                                    float* __restrict__ gV_out) {
+                                                    float* __restrict__ gV_out, SegDst seg) {
   constexpr int LPR = K / 4;
   constexpr int G = 32 / LPR;
   constexpr int NPASS = 32 / G;
@@ -635,7 +636,13 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
       }
       if (s < 0) vr = -1;
     } else if (active) {
-      gw_out[i] = gw;
+      if (seg.nseg == 0) {
+        gw_out[i] = gw;
+      } else {   // the owner's receive buffer (peer memory over NVLink)
+        int sg = 0;
+        while (sg + 1 < seg.nseg && (int)i >= seg.bounds[sg + 1]) ++sg;
+        seg.gw[sg][i - (size_t)seg.bounds[sg]] = gw;
+      }
       if (acc_pen) pen += pen_w(p, slot ? __int_as_float(slot[i]) : 0.f);   // worker: slot aliases the pulled w
     }
     // ---------------- phase B: the table rows, G keys per pass ----------------
@@ -698,7 +705,13 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
           const size_t ik = base + (size_t)((pass + q) * G + grp);
           const float xp = xxpk[q];
           if (acc_pen) pen += 0.5f * p.V_l2 * (v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w);
-          *reinterpret_cast<float4*>(gV_out + ik * (size_t)K + sub * 4) =
+          float* grow = gV_out + ik * (size_t)K;
+          if (seg.nseg != 0) {
+            int sg = 0;
+            while (sg + 1 < seg.nseg && (int)ik >= seg.bounds[sg + 1]) ++sg;
+            grow = seg.gV[sg] + (ik - (size_t)seg.bounds[sg]) * (size_t)K;
+          }
+          *reinterpret_cast<float4*>(grow + sub * 4) =
               make_float4(__fsub_rn(g[q].x, __fmul_rn(v[q].x, xp)), __fsub_rn(g[q].y, __fmul_rn(v[q].y, xp)),
                           __fsub_rn(g[q].z, __fmul_rn(v[q].z, xp)), __fsub_rn(g[q].w, __fmul_rn(v[q].w, xp)));
         }
@@ -789,10 +802,10 @@ int launch_pack_ragged(Table& t, const Params& p, const int* slot, size_t n, int
   return 4;
 }
 
-int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* hasv_out, float* V_out,
-                       cudaStream_t s) {
+int launch_gather_rows(Table& t, const int* slot, size_t n, float* w_out, int* hasv_out, int* hasv_out2,
+                       float* V_out, cudaStream_t s) {
   if (n == 0) return 0;
-  k_gather_rows<<<grid_warps((n + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, slot, n, w_out, hasv_out, V_out);
+  k_gather_rows<<<grid_warps((n + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, slot, n, w_out, hasv_out, hasv_out2, V_out);
   return 1;
 }
 
@@ -892,13 +905,15 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
                       const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
                       const float* p_row, const float* pxv, int* flags, int acc_pen, cudaStream_t s) {
   if (n == 0) return 0;
+  SegDst noseg;
+  memset(&noseg, 0, sizeof(noseg));
 #define DFB_BU(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
     if (valued) k_bwd_update<K, true, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end, \
-                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr);                      \
+                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg);               \
     else k_bwd_update<K, false, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end,     \
-                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr);                      \
+                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg);               \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_BU(8); return 1;
@@ -914,19 +929,21 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
 int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_pulled, const int* hasv, size_t n,
                      const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
                      const float* p_row, const float* pxv, float* gw_out, const float* V_pulled, float* gV_out,
-                     int acc_pen, cudaStream_t s) {
+                     int acc_pen, const SegDst* seg, cudaStream_t s) {
   if (n == 0) return 0;
   if (ks != p.V_dim) return -1;
   Table t;
   t.prog = prog;
+  SegDst sd;
+  if (seg) sd = *seg; else memset(&sd, 0, sizeof(sd));
   const int* w_alias = reinterpret_cast<const int*>(w_pulled);
 #define DFB_BD(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
     if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, col_start, col_end, \
-                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out);                     \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd);                 \
     else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, col_start, col_end,      \
-                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out);                     \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd);                 \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_BD(8); return 1;
@@ -944,11 +961,13 @@ int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_
 int launch_update_pushed(Table& t, const Params& p, const int* slot, const int* hasv, size_t n, const float* gw,
                          const float* gV, int* flags, cudaStream_t s) {
   if (n == 0) return 0;
+  SegDst noseg;
+  memset(&noseg, 0, sizeof(noseg));
 #define DFB_UP(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
     k_bwd_update<K, false, true, 1><<<grid, 256, 0, s>>>(t, p, slot, hasv, n, nullptr, nullptr, nullptr, gw, \
-                                                          gV, flags, 0, nullptr, nullptr, nullptr);         \
+                                                          gV, flags, 0, nullptr, nullptr, nullptr, noseg);  \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_UP(8); return 1;

@@ -188,6 +188,120 @@ class ShardedStore:
         self._mark("owner_update")
 
 
+class PeerShardedStore(ShardedStore):
+    """Same protocol, but the two row exchanges are fused into the kernels that produce the rows:
+    the owner's gather kernel stores {w, has_V, V} straight into the requester's pull buffer and the
+    worker's gradient kernel stores {gw, gV} straight into the owner's receive buffer, through
+    peer pointers over NVLink (CUDA IPC, one process per GPU).  NCCL carries only the key lists,
+    the count matrix and two tiny barriers per step.  Needs the engine's sorted scatter path
+    (V_dim in {8,16,32,64,128}); otherwise use ShardedStore."""
+
+    def __init__(self, backend, max_keys, max_recv_keys=None, group=None):
+        super().__init__(backend, group)
+        E = backend.E
+        S, ks = self.S, self.ks
+        self.Umax = int(max_keys)
+        self.Rmax = int(max_recv_keys if max_recv_keys is not None else max_keys * 1.5 + 1024)
+        al = lambda n: (int(n) + 255) // 256 * 256
+        # pull buffer (owners store into it): w | hasv | V
+        self.off_hasv = al(self.Umax * 4)
+        self.off_V = self.off_hasv + al(self.Umax * 4)
+        pull_bytes = self.off_V + al(self.Umax * ks * 4)
+        # push buffer (workers store into it): gw | gV
+        self.off_gV = al(self.Rmax * 4)
+        push_bytes = self.off_gV + al(self.Rmax * ks * 4)
+        self.pull_ptr, pull_h = E.peer_alloc(pull_bytes)
+        self.push_ptr, push_h = E.peer_alloc(push_bytes)
+        handles = [None] * S
+        if S > 1:
+            dist.all_gather_object(handles, (pull_h, push_h), group=self.group)
+        self.pull_peer, self.push_peer = [], []
+        for r in range(S):
+            if r == self.rank:
+                self.pull_peer.append(self.pull_ptr)
+                self.push_peer.append(self.push_ptr)
+            else:
+                self.pull_peer.append(E.peer_open(handles[r][0]))
+                self.push_peer.append(E.peer_open(handles[r][1]))
+        dev = backend.device
+        self._tick = torch.zeros(1, device=dev)
+        self.hasv_r = torch.empty(self.Rmax, dtype=torch.int32, device=dev)
+        if S > 1:
+            dist.barrier(group=self.group)
+
+    def _barrier(self):
+        if self.S > 1:
+            dist.all_reduce(self._tick, group=self.group)
+
+    def step(self, batch, is_train=True, push_cnt=False):
+        S, U, ks, me, E = self.S, batch["U"], self.ks, self.rank, self.b.E
+        assert U <= self.Umax, "batch has more keys than the pull buffer (max_keys)"
+        self._mark("begin")
+        bounds = [int(x) for x in batch["bounds"]]
+        send = [bounds[i + 1] - bounds[i] for i in range(S)]
+        dev = batch["keys"].device
+        if S == 1:
+            M = [send]
+        else:
+            t_send = torch.tensor(send, dtype=torch.int64, device=dev)
+            t_all = torch.empty(S * S, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(t_all, t_send, group=self.group)
+            M = t_all.view(S, S).tolist()          # M[r][s] = keys rank r sends to owner s
+        recv = [int(M[r][me]) for r in range(S)]
+        R = sum(recv)
+        assert R <= self.Rmax, "more keys received than the push buffer holds (max_recv_keys)"
+        seg = [0]
+        for r in range(S):
+            seg.append(seg[-1] + recv[r])
+        keys_r = self._get("keys_r", R, (), torch.int64)
+        self._a2a(keys_r, batch["keys"], recv, send)
+        self._mark("a2a_counts_keys")
+        if push_cnt:
+            cnt_r = self._get("cnt_r", R, (), torch.float32)
+            self._a2a(cnt_r, batch["cnt"], recv, send)
+            for src in range(S):
+                self.b.feacnt(keys_r[seg[src]:seg[src + 1]], cnt_r[seg[src]:seg[src + 1]])
+        # ---- Pull: gather + store into the requester's buffer (its key order = owner order) ----
+        for src in range(S):
+            n = recv[src]
+            if n == 0:
+                continue
+            off = sum(int(M[src][s]) for s in range(me))     # = requester's bounds[me]
+            base = self.pull_peer[src]
+            E.dev_pull_rows_peer(keys_r[seg[src]:seg[src + 1]], n, base + off * 4, base + self.off_hasv + off * 4,
+                                 base + self.off_V + off * ks * 4, self.hasv_r[seg[src]:seg[src + 1]])
+        self._barrier()
+        self._mark("pull_gather_store")
+        w, hasv, V = self.pull_ptr, self.pull_ptr + self.off_hasv, self.pull_ptr + self.off_V
+        # ---- Predict / Evaluate / CalcGrad; gradient rows stored into the owners' buffers ----
+        if not is_train:
+            gw = self._get("gw", U, (), torch.float32)
+            gV = self._get("gV", U, (ks,), torch.float32)
+            E.dev_fm_step(batch["nrows"], batch["nnz"], batch["off"], batch["lidx"], batch.get("val"), batch["lab"], U,
+                          w, hasv, V, False, gw, gV)
+            self._barrier()     # nobody overwrites this pull buffer before every worker is done with it
+            self._mark("worker_fm")
+            return
+        pgw, pgV = [], []
+        for s in range(S):
+            off = sum(int(M[r][s]) for r in range(me))        # where my segment starts at owner s
+            pgw.append(self.push_peer[s] + off * 4)
+            pgV.append(self.push_peer[s] + self.off_gV + off * ks * 4)
+        E.dev_fm_step_peer(batch["nrows"], batch["nnz"], batch["off"], batch["lidx"], batch.get("val"), batch["lab"], U,
+                           w, hasv, V, bounds, pgw, pgV)
+        self._barrier()
+        self._mark("worker_fm_store")
+        # ---- Push(kGradient): one Update per worker, rank order ----
+        for src in range(S):
+            n = recv[src]
+            if n == 0:
+                continue
+            a = seg[src]
+            E.dev_push_rows(keys_r[a:a + n], n, self.push_ptr + a * 4, self.hasv_r[a:a + n],
+                            self.push_ptr + self.off_gV + a * ks * 4)
+        self._mark("owner_update")
+
+
 # ---------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): one process per GPU, launched by torch.distributed.run
 # ---------------------------------------------------------------------------------------------
@@ -221,7 +335,21 @@ def bench_main(args, rank, world, local_rank, benchmod):
     cap = int(nb * U_mean * 1.15) + 4096
     E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap, **kw)
     backend = CudaBackend(E, dev)
-    store = ShardedStore(backend)
+    use_p2p = os.environ.get("DFB_SHARDED", "p2p") == "p2p" and E.V_dim in (8, 16, 32, 64, 128)
+    store = None
+    if use_p2p:
+        Umax = int(max(h["U"] for h in host) * 1.02) + 1024
+        ok = 1
+        try:
+            store = PeerShardedStore(backend, max_keys=Umax, max_recv_keys=int(Umax * 1.3))
+        except Exception as e:      # e.g. CUDA IPC unavailable: every rank falls back together
+            print(f"[rank {rank}] peer store unavailable ({e!r}); using NCCL all_to_all", flush=True)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use_p2p = bool(flag.item())
+    if not use_p2p:
+        store = ShardedStore(backend)
 
     def to_dev(h):
         d = dict(h)
@@ -305,8 +433,12 @@ def bench_main(args, rank, world, local_rank, benchmod):
             "config": benchmod.workload_config(args, {
                 "unique_keys_per_batch": int(U_mean), "working_set_batches": nb,
                 "parallelism": f"dp{world} minibatches x table sharded by reversed-key range over {world} GPUs "
-                               "(ps-lite rule), Pull/Push = NCCL all_to_all of the active rows"}),
-            "roofline": {"bound": "nvlink", "kernel": "all_to_all of active rows (pull + push)",
+                               "(ps-lite rule), Pull/Push of the active rows = "
+                               + ("peer stores over NVLink fused into the gather / gradient kernels (CUDA IPC)"
+                                  if use_p2p else "NCCL all_to_all")}),
+            "roofline": {"bound": "nvlink", "kernel": ("k_gather_rows -> peer pull buffer + k_bwd_update<dense> -> peer push buffer "
+                                                       "(fused compute + NVLink stores)" if use_p2p else
+                                                       "all_to_all of active rows (pull + push)"),
                          "achieved": a2a_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": nvl, "unit": "GB/s",
                          "frac": a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / nvl, "traffic": None,
                          "algorithmic_bytes": int(a2a_bytes),

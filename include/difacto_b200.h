@@ -228,6 +228,26 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_of
                     int is_train, float* d_gw_out, float* d_gV_out);
 int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const float* d_gw,
                       const int* d_hasv, const float* d_gV);
+/* NVLink peer-store variants (one process per GPU, buffers shared through CUDA IPC):
+ *   dfb_peer_alloc / dfb_peer_open   a device buffer + its 64-byte cudaIpcMemHandle_t; a peer process opens
+ *                                    the handle and gets a pointer its kernels can store through
+ *   dfb_dev_pull_rows_peer           owner: gather {w, has_V, V} for one requester's key segment and store the
+ *                                    rows straight into the requester's pull buffer (fused gather + transfer);
+ *                                    the pull-time has_V flags are also kept locally for the later push
+ *   dfb_dev_fm_step_peer             worker: as dfb_dev_fm_step (training), but the gradient rows of key
+ *                                    segment s (keys [seg_bounds[s], seg_bounds[s+1])) are stored straight into
+ *                                    owner s's receive buffer (peer_gw[s], peer_gV[s] = where the segment starts) */
+int dfb_peer_alloc(dfb_handle h, size_t bytes, void** ptr, unsigned char* handle64);
+int dfb_peer_open(dfb_handle h, const unsigned char* handle64, void** ptr);
+int dfb_peer_close(dfb_handle h, void* ptr);
+int dfb_peer_free(dfb_handle h, void* ptr);
+int dfb_dev_pull_rows_peer(dfb_handle h, const uint64_t* d_keys, size_t n, float* peer_w_out,
+                           int* peer_hasv_out, float* peer_V_out, int* d_hasv_local_out);
+int dfb_dev_fm_step_peer(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset,
+                         const uint32_t* d_index, const float* d_value_or_null, const float* d_label,
+                         size_t nkeys, const float* d_w, const int* d_hasv, const float* d_V, int nseg,
+                         const size_t* seg_bounds, float* const* peer_gw, float* const* peer_gV);
+
 /* the CUDA stream (cudaStream_t) the handle enqueues on, for event interop with torch */
 void* dfb_stream(dfb_handle h);
 

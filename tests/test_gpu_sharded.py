@@ -39,16 +39,19 @@ def make_batch(rank, step, valued, S, dev, B=96, ids=500, max_nnz=24):
     return d, host
 
 
-@pytest.mark.parametrize("V_dim,scatter", [(16, "sorted"), (16, "atomic"), (6, "sorted"), (0, "sorted")])
+@pytest.mark.parametrize("V_dim,scatter", [(16, "sorted"), (16, "atomic"), (6, "sorted"), (0, "sorted"), (16, "p2p")])
 def test_single_rank_sharded_equals_fused_and_oracle(V_dim, scatter):
-    from difacto_b200.sharded import CudaBackend, ShardedStore
+    from difacto_b200.sharded import CudaBackend, PeerShardedStore, ShardedStore
+    p2p = scatter == "p2p"
+    if p2p:
+        scatter = "sorted"
     dev = torch.device("cuda", 0)
     kw = dict(V_dim=V_dim, l1=0.05, l2=0.01, lr=0.2, V_lr=0.1, V_threshold=1, V_l2=0.01, V_init_scale=0.2, seed=3)
     E1 = capi.Engine(table_capacity=1 << 14, scatter=scatter, **kw)     # behind the sharded protocol (S = 1)
     E2 = capi.Engine(table_capacity=1 << 14, scatter=scatter, **kw)     # fused single-engine step
     M = O.Oracle(**kw)
     be = CudaBackend(E1, dev)
-    store = ShardedStore(be)
+    store = PeerShardedStore(be, max_keys=4096) if p2p else ShardedStore(be)
     allkeys = []
     with torch.cuda.stream(be.stream):
         for step in range(8):
@@ -84,10 +87,10 @@ KW2 = dict(V_dim=16, l1=0.05, l2=0.01, lr=0.2, V_lr=0.1, V_threshold=1, V_l2=0.0
 STEPS2 = 6
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, p2p):
     import torch.distributed as dist
     from difacto_b200 import capi as C2
-    from difacto_b200.sharded import CudaBackend, ShardedStore, key_owner_np
+    from difacto_b200.sharded import CudaBackend, PeerShardedStore, ShardedStore, key_owner_np
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -95,7 +98,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     E = C2.Engine(device=rank, table_capacity=1 << 14, **KW2)
     be = CudaBackend(E, dev)
-    store = ShardedStore(be)
+    store = PeerShardedStore(be, max_keys=4096) if p2p else ShardedStore(be)
     prog = np.zeros(2)
     with torch.cuda.stream(be.stream):
         for step in range(STEPS2):
@@ -113,13 +116,14 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpu_nccl_sharded_vs_oracle_simulation(tmp_path):
+@pytest.mark.parametrize("p2p", [False, True])
+def test_two_gpu_nccl_sharded_vs_oracle_simulation(tmp_path, p2p):
     import torch.multiprocessing as mp
     from difacto_b200.sharded import key_owner_np
     from oracle_backend import OracleBackend
     world = 2
     out = str(tmp_path / "shard{rank}.npz")
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, p2p), nprocs=world, join=True)
     # sequential simulation with oracle shards (same protocol semantics)
     cpu = torch.device("cpu")
     shards = [OracleBackend(**KW2) for _ in range(world)]
