@@ -350,6 +350,37 @@ def main_b200(args, rank, world, local_rank):
                "d2h_bytes_per_step": 64, "ms_per_step": dt / args.steps * 1e3,
                "api": "dfb_train_step_async + dfb_wait_step (C-ABI), localized CSR + keys from pinned host memory",
                "mean_loss_per_step": loss_sum / args.steps}
+    # ---- e2e from RAW ids: Localizer::Compact runs on the GPU inside the timed region ----
+    e2e_raw = None
+    if not args.no_e2e:
+        raw = []
+        for b in range(nb):
+            off, lab, ids = gen_raw_batch(args, 1 + b)
+            raw.append(dict(off=torch.from_numpy(off).pin_memory(), lab=torch.from_numpy(lab).pin_memory(),
+                            ids=torch.from_numpy(ids.view(np.int64)).pin_memory()))
+
+        def submit_raw(b):
+            r = raw[b]
+            E.train_step_raw_async(B, r["off"], r["ids"], None, r["lab"], False, True)
+        for t in range(args.warmup):
+            submit_raw(t % nb)
+        E.read_progress()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss_sum = 0.0
+        for t in range(args.steps):
+            submit_raw((args.warmup + t) % nb)
+            if t >= 1:
+                loss_sum += E.wait_step().loss
+        loss_sum += E.wait_step().loss
+        E.sync()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_raw = {"value": args.steps * B / dt, "unit": "examples/s",
+                   "h2d_bytes_per_step": int((B + 1) * 8 + N * 8 + B * 4), "d2h_bytes_per_step": 64 + 16,
+                   "ms_per_step": dt / args.steps * 1e3,
+                   "api": "dfb_train_step_raw_async + dfb_wait_step: raw uint64 CSR from pinned host memory, "
+                          "Localizer::Compact on the GPU, then the fused step"}
     sampler.stop()
     clocks = sampler.summary(wall0, time.time())   # value + stage + forward-only + e2e regions: all under load
 
@@ -423,7 +454,7 @@ def main_b200(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, {"unique_keys_per_batch": int(U_mean), "working_set_batches": nb,
                                          "table_keys": int(total_keys), "parallelism": "1 gpu, table resident in HBM"}),
-        "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_raw_ids": e2e_raw,
         "gpu_launches": int(launches), "clocks": clocks,
         "stages_ms_per_step": {n: s["ms"] / max(s["count"], 1) for n, s in stages.items()},
         "loss_per_example": prog.loss / max(prog.nrows, 1), "datagen_s": t_gen,

@@ -33,7 +33,8 @@ EXPORTS = [
     "dfb_dev_feacnt", "dfb_dev_pull_rows", "dfb_dev_fm_step", "dfb_dev_push_rows", "dfb_stream",
     "dfb_wait_step", "dfb_profile", "dfb_profile_read",
     "dfb_peer_alloc", "dfb_peer_open", "dfb_peer_close", "dfb_peer_free", "dfb_dev_pull_rows_peer",
-    "dfb_dev_fm_step_peer",
+    "dfb_dev_fm_step_peer", "dfb_localize", "dfb_train_step_raw", "dfb_train_step_raw_async",
+    "dfb_train_step_raw_dev",
 ]
 
 _LIB = None
@@ -89,6 +90,10 @@ def lib():
         L.dfb_peer_free.argtypes = [vp, vp]
         L.dfb_dev_pull_rows_peer.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         L.dfb_dev_fm_step_peer.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp, vp]
+        L.dfb_localize.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, C.POINTER(sz)]
+        L.dfb_train_step_raw.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Progress), vp]
+        L.dfb_train_step_raw_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_train_step_raw_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, C.c_int, C.c_int]
         L.dfb_stream.restype = vp
         L.dfb_stream.argtypes = [vp]
         _LIB = L
@@ -250,6 +255,37 @@ class Engine:
         self._ck(self.L.dfb_train_step(self.h, nrows, _p(offset), _p(lidx), _p(value), _p(label), _p(keys),
                                        len(keys), _p(cnt), int(is_train), C.byref(pr), _p(pred)))
         return (pr, pred[:nrows]) if want_pred else pr
+
+    # ---- raw ids: GPU localizer + fused step ----
+    def localize(self, offset, index, max_index=0xFFFFFFFFFFFFFFFF, want_cnt=True):
+        offset, index = _arr(offset, np.uint64), _arr(index, np.uint64)
+        nrows = len(offset) - 1
+        nnz = int(offset[-1]) if nrows > 0 else 0
+        lidx = np.zeros(max(nnz, 1), np.uint32)
+        keys = np.zeros(max(nnz, 1), np.uint64)
+        cnt = np.zeros(max(nnz, 1), np.float32) if want_cnt else None
+        n = C.c_size_t()
+        self._ck(self.L.dfb_localize(self.h, nrows, _p(offset), _p(index), max_index, _p(lidx), _p(keys), _p(cnt),
+                                     C.byref(n)))
+        return lidx[:nnz], keys[:n.value].copy(), (cnt[:n.value].copy() if want_cnt else None)
+
+    def train_step_raw(self, offset, ids, value, label, push_cnt=False, is_train=True, want_pred=False):
+        offset, ids = _arr(offset, np.uint64), _arr(ids, np.uint64)
+        value, label = _arr(value, np.float32), _arr(label, np.float32)
+        nrows = len(offset) - 1
+        pr = Progress()
+        pred = np.zeros(max(nrows, 1), np.float32) if want_pred else None
+        self._ck(self.L.dfb_train_step_raw(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label), int(push_cnt),
+                                           int(is_train), C.byref(pr), _p(pred)))
+        return (pr, pred[:nrows]) if want_pred else pr
+
+    def train_step_raw_async(self, nrows, offset, ids, value, label, push_cnt=False, is_train=True):
+        self._ck(self.L.dfb_train_step_raw_async(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label),
+                                                 int(push_cnt), int(is_train)))
+
+    def train_step_raw_dev(self, nrows, nnz, d_offset, d_ids, d_value, d_label, push_cnt=False, is_train=True):
+        self._ck(self.L.dfb_train_step_raw_dev(self.h, nrows, nnz, _p(d_offset), _p(d_ids), _p(d_value), _p(d_label),
+                                               int(push_cnt), int(is_train)))
 
     def train_step_async(self, nrows, offset, lidx, value, label, keys, nkeys, cnt=None, is_train=True):
         """raw pointers / arrays, no conversion: for pinned-memory pipelines"""

@@ -169,6 +169,18 @@ int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp, 
 int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* hasv, float* V,
                         float* cg, int k, cudaStream_t s);
 
+// ---- GPU localizer (kernels_localize.cu): Localizer::Compact + the CSC view from one radix sort ----
+size_t localize_sort_tmp_bytes(size_t nnz);
+int launch_localize_keys(const uint64_t* ids, size_t nnz, uint64_t max_index, unsigned long long* rkeys,
+                         uint32_t* pos, unsigned long long* or_all, const uint64_t* offset, size_t nrows,
+                         uint32_t* nnz_row, cudaStream_t s);
+int launch_localize_sort(const unsigned long long* rkeys, const uint32_t* pos, size_t nnz, int begin_bit,
+                         unsigned long long* skeys, uint32_t* spos, int* head, int* rank1, void* tmp,
+                         size_t tmp_bytes, const uint32_t* nnz_row, const float* value, uint64_t* keys_out,
+                         int* col_start, int* col_end, uint32_t* lidx_out, void* occ_sorted,
+                         unsigned long long* n_unique, cudaStream_t s);
+int launch_cnt_from_cols(const int* col_start, const int* col_end, size_t n, float* cnt, cudaStream_t s);
+
 // ---- sorted (atomic-free, deterministic) gradient reduction ----
 // CSC view of the batch: stable radix sort of (local key id -> occurrence payload); afterwards
 // key u owns occ_sorted[col_start[u] .. col_end[u]) in row order (the reference's summation

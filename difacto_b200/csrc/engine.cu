@@ -50,10 +50,12 @@ struct dfb_engine {
   DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
   DevBuf auc_k, auc_v, auc_tmp;
   DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
+  DevBuf l_rkeys, l_skeys, l_pos, l_spos, l_head, l_rank, l_nnzrow, l_keys, l_lidx, l_cnt, l_scal, l_tmp;
+  unsigned long long* h_scal = nullptr;   // pinned: {or_all, n_unique}
   DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
   DevBuf scal, hasv, rV, rcg, nvals;
   // double-buffered inputs of the pipelined step
-  struct InSet { DevBuf off, idx, val, lab, keys, cnt; cudaEvent_t copied = nullptr, consumed = nullptr; } in[2];
+  struct InSet { DevBuf off, idx, val, lab, keys, cnt, ids; cudaEvent_t copied = nullptr, consumed = nullptr; } in[2];
   uint64_t seq = 0;
   // per-step Progress snapshots of the pipelined path (pinned ring + completion events)
   static constexpr int kRing = 4;
@@ -259,7 +261,7 @@ int ensure_sorted_ws(dfb_engine* h, size_t nrows, size_t nnz, size_t U, bool val
 
 int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint32_t* d_idx,
              const float* d_val, const float* d_lab, const uint64_t* d_keys, size_t U, const float* d_cnt,
-             int is_train) {
+             int is_train, bool csc_ready = false) {
   if (U > 0x7fffffffULL || nrows > 0x7fffffffULL || nnz > 0x7fffffffULL)
     return h->fail(DFB_ERR_INVALID, "batch too large");
   const bool sorted = is_train && h->scatter_sorted && !h->force_generic && fm_fast_supported(h->prm.V_dim);
@@ -312,7 +314,8 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   b.V_dim = h->prm.V_dim; b.train = is_train; b.prog = h->tab.prog;
   if (sorted) {
     b.emit = 1; b.p_out = h->p_row.as<float>(); b.pxv_out = h->pxv.as<float>();
-    b.occ_row = h->occ.as<uint32_t>(); b.occ_rowx = h->occ.as<unsigned long long>();
+    b.occ_row = csc_ready ? nullptr : h->occ.as<uint32_t>();
+    b.occ_rowx = csc_ready ? nullptr : h->occ.as<unsigned long long>();
   }
   if (nrows) {
     StageTimer tm(h, 1);
@@ -345,9 +348,10 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
     // CalcGrad + Push(kGradient) without materialising the gradient: CSC view of the batch, then
     // per key reduce + FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
     StageTimer tm(h, 3);
-    h->launches += launch_csc_build(d_idx, h->occ.p, d_val != nullptr, nnz, U, h->lidx_sorted.as<uint32_t>(),
-                                    h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
-                                    h->cub.bytes, s);
+    if (!csc_ready)
+      h->launches += launch_csc_build(d_idx, h->occ.p, d_val != nullptr, nnz, U, h->lidx_sorted.as<uint32_t>(),
+                                      h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
+                                      h->cub.bytes, s);
   }
   StageTimer tm_upd(h, 4);
   if (sorted) {
@@ -382,6 +386,67 @@ int collect_one(dfb_engine* h, DevProgress* acc) {
   add_prog(*acc, h->h_ring[r]);
   h->collected++;
   return 0;
+}
+
+// Localizer::Compact on the device.  Leaves keys in l_keys, the remapped CSR index in l_lidx and the CSC
+// view in occ_sorted / col_start / col_end; returns the number of unique keys (two small D2H syncs:
+// the significant key-bit range for the radix sort, then the unique count).
+int localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
+                 const float* d_val, uint64_t max_index, size_t* U_out) {
+  cudaStream_t s = h->stream;
+  *U_out = 0;
+  if (nnz > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "batch too large");   // localizer.cc:19-20
+  if (max_index == 0) return h->fail(DFB_ERR_INVALID, "max_index must be > 0");
+  const size_t n1 = nnz ? nnz : 1;
+  DFB_TRY(h->ensure(h->l_rkeys, n1 * 8));
+  DFB_TRY(h->ensure(h->l_skeys, n1 * 8));
+  DFB_TRY(h->ensure(h->l_pos, n1 * 4));
+  DFB_TRY(h->ensure(h->l_spos, n1 * 4));
+  DFB_TRY(h->ensure(h->l_head, n1 * 4));
+  DFB_TRY(h->ensure(h->l_rank, n1 * 4));
+  DFB_TRY(h->ensure(h->l_nnzrow, n1 * 4));
+  DFB_TRY(h->ensure(h->l_keys, n1 * 8));
+  DFB_TRY(h->ensure(h->l_lidx, n1 * 4));
+  DFB_TRY(h->ensure(h->l_cnt, n1 * 4));
+  DFB_TRY(h->ensure(h->l_scal, 16));
+  DFB_TRY(h->ensure(h->l_tmp, localize_sort_tmp_bytes(nnz)));
+  DFB_TRY(h->ensure(h->occ_sorted, n1 * (d_val ? 8 : 4)));
+  DFB_TRY(h->ensure(h->col_start, n1 * 4));
+  DFB_TRY(h->ensure(h->col_end, n1 * 4));
+  if (nnz == 0) return 0;
+  unsigned long long* scal = h->l_scal.as<unsigned long long>();
+  h->launches += launch_localize_keys(d_ids, nnz, max_index, h->l_rkeys.as<unsigned long long>(),
+                                      h->l_pos.as<uint32_t>(), scal, d_off, nrows, h->l_nnzrow.as<uint32_t>(), s);
+  DFB_CUDA(h, cudaMemcpyAsync(h->h_scal, scal, 8, cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaStreamSynchronize(s));
+  const unsigned long long or_all = h->h_scal[0];
+  int begin_bit = 0;
+  if (or_all) { while (((or_all >> begin_bit) & 1ULL) == 0) ++begin_bit; }
+  else begin_bit = 63;    // every key is 0
+  h->launches += launch_localize_sort(h->l_rkeys.as<unsigned long long>(), h->l_pos.as<uint32_t>(), nnz, begin_bit,
+                                      h->l_skeys.as<unsigned long long>(), h->l_spos.as<uint32_t>(),
+                                      h->l_head.as<int>(), h->l_rank.as<int>(), h->l_tmp.p, h->l_tmp.bytes,
+                                      h->l_nnzrow.as<uint32_t>(), d_val, h->l_keys.as<uint64_t>(),
+                                      h->col_start.as<int>(), h->col_end.as<int>(), h->l_lidx.as<uint32_t>(),
+                                      h->occ_sorted.p, scal + 1, s);
+  DFB_CUDA(h, cudaMemcpyAsync(h->h_scal + 1, scal + 1, 8, cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaStreamSynchronize(s));
+  *U_out = (size_t)h->h_scal[1];
+  return 0;
+}
+
+// raw (un-localized) CSR<u64> minibatch: Localizer::Compact + the fused step, all on the device
+int step_raw_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
+                 const float* d_val, const float* d_lab, int push_cnt, int is_train) {
+  size_t U = 0;
+  DFB_TRY(localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, &U));   // Localizer(-1, ...), sgd_learner.cc:203
+  const float* d_cnt = nullptr;
+  if (push_cnt && U) {
+    h->launches += launch_cnt_from_cols(h->col_start.as<int>(), h->col_end.as<int>(), U, h->l_cnt.as<float>(), h->stream);
+    d_cnt = h->l_cnt.as<float>();
+  }
+  return step_dev(h, nrows, nnz, d_off, h->l_lidx.as<uint32_t>(), d_val, d_lab, h->l_keys.as<uint64_t>(), U, d_cnt,
+                  is_train, /*csc_ready=*/true);
 }
 
 int check_csr(dfb_engine* h, size_t nrows, const uint64_t* offset) {
@@ -490,6 +555,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   if ((e = cudaHostAlloc(&h->h_prog, sizeof(DevProgress), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   if ((e = cudaHostAlloc(&h->h_nvals, sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   memset(h->h_prog, 0, sizeof(DevProgress));
+  if ((e = cudaHostAlloc(&h->h_scal, 2 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   if ((e = cudaHostAlloc(&h->h_ring, dfb_engine::kRing * sizeof(DevProgress), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   memset(h->h_ring, 0, dfb_engine::kRing * sizeof(DevProgress));
   memset(&h->backlog, 0, sizeof(DevProgress));
@@ -505,14 +571,15 @@ int dfb_destroy(dfb_handle h) {
   if (!h) return DFB_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
+  DevBuf* bufs[] = {&h->l_rkeys, &h->l_skeys, &h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow, &h->l_keys,
+                    &h->l_lidx, &h->l_cnt, &h->l_scal, &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
                     &h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
                     &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
                     &h->a_val, &h->a_lab, &h->a_w, &h->a_wpos, &h->a_vpos, &h->a_pred, &h->a_grad, &h->scal,
                     &h->hasv, &h->rV, &h->rcg, &h->nvals};
   for (auto* b : bufs) if (b->p) cudaFree(b->p);
   for (auto& s : h->in) {
-    DevBuf* ib[] = {&s.off, &s.idx, &s.val, &s.lab, &s.keys, &s.cnt};
+    DevBuf* ib[] = {&s.off, &s.idx, &s.val, &s.lab, &s.keys, &s.cnt, &s.ids};
     for (auto* b : ib) if (b->p) cudaFree(b->p);
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.consumed) cudaEventDestroy(s.consumed);
@@ -524,6 +591,7 @@ int dfb_destroy(dfb_handle h) {
   if (h->h_prog) cudaFreeHost(h->h_prog);
   if (h->h_nvals) cudaFreeHost(h->h_nvals);
   if (h->h_ring) cudaFreeHost(h->h_ring);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
   for (auto& ev : h->ring_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->pev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -836,6 +904,8 @@ int dfb_read_progress(dfb_handle h, dfb_progress* out) {
   return check_dev_err(h);
 }
 
+static int snapshot_step(dfb_handle h);
+
 int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index,
                          const float* value, const float* label, const uint64_t* keys, size_t nkeys,
                          const float* cnt, int is_train) {
@@ -864,14 +934,7 @@ int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, con
   DFB_CUDA(h, cudaEventRecord(in.consumed, h->stream));
   h->seq++;
   if (rc != 0) return rc;
-  // per-step snapshot of the Progress block: D2H into the pinned ring, then clear
-  if (h->submitted - h->collected == (uint64_t)dfb_engine::kRing) DFB_TRY(collect_one(h, &h->backlog));
-  const int r = (int)(h->submitted % dfb_engine::kRing);
-  DFB_CUDA(h, cudaMemcpyAsync(&h->h_ring[r], h->tab.prog, sizeof(DevProgress), cudaMemcpyDeviceToHost, h->stream));
-  DFB_CUDA(h, cudaMemsetAsync(h->tab.prog, 0, sizeof(DevProgress), h->stream));
-  DFB_CUDA(h, cudaEventRecord(h->ring_done[r], h->stream));
-  h->submitted++;
-  return DFB_OK;
+  return snapshot_step(h);   // per-step snapshot of the Progress block: D2H into the pinned ring, then clear
 }
 
 int dfb_wait_step(dfb_handle h, dfb_progress* out) {
@@ -909,6 +972,83 @@ int dfb_profile_read(dfb_handle h, double* stage_ms, uint64_t* stage_count) {
   }
   h->prof_steps = 0;
   return DFB_OK;
+}
+
+// snapshot of the Progress block into the pinned ring (shared by the async entry points)
+static int snapshot_step(dfb_handle h) {
+  if (h->submitted - h->collected == (uint64_t)dfb_engine::kRing) DFB_TRY(collect_one(h, &h->backlog));
+  const int r = (int)(h->submitted % dfb_engine::kRing);
+  DFB_CUDA(h, cudaMemcpyAsync(&h->h_ring[r], h->tab.prog, sizeof(DevProgress), cudaMemcpyDeviceToHost, h->stream));
+  DFB_CUDA(h, cudaMemsetAsync(h->tab.prog, 0, sizeof(DevProgress), h->stream));
+  DFB_CUDA(h, cudaEventRecord(h->ring_done[r], h->stream));
+  h->submitted++;
+  return DFB_OK;
+}
+
+int dfb_localize(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* index, uint64_t max_index,
+                 uint32_t* index_out, uint64_t* keys_out, float* cnt_out, size_t* nkeys) {
+  if (!h || !nkeys) return DFB_ERR_INVALID;
+  *nkeys = 0;
+  DFB_TRY(check_csr(h, nrows, offset));
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
+  if (nnz == 0) return DFB_OK;                       // localizer.cc:16
+  if (!index || !index_out || !keys_out) return h->fail(DFB_ERR_INVALID, "NULL argument");
+  cudaStream_t s = h->stream;
+  DFB_TRY(h2d(h, h->a_off, offset, (nrows + 1) * sizeof(uint64_t), s));
+  DFB_TRY(h2d(h, h->keys, index, nnz * sizeof(uint64_t), s));
+  size_t U = 0;
+  DFB_TRY(localize_dev(h, nrows, nnz, h->a_off.as<uint64_t>(), h->keys.as<uint64_t>(), nullptr, max_index, &U));
+  DFB_CUDA(h, cudaMemcpyAsync(index_out, h->l_lidx.p, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaMemcpyAsync(keys_out, h->l_keys.p, U * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  if (cnt_out) {
+    h->launches += launch_cnt_from_cols(h->col_start.as<int>(), h->col_end.as<int>(), U, h->l_cnt.as<float>(), s);
+    DFB_CUDA(h, cudaMemcpyAsync(cnt_out, h->l_cnt.p, U * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  DFB_CUDA(h, cudaStreamSynchronize(s));
+  *nkeys = U;
+  return DFB_OK;
+}
+
+int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint64_t* d_ids,
+                           const float* d_value_or_null, const float* d_label, int push_cnt, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  return step_raw_dev(h, nrows, nnz, d_offset, d_ids, d_value_or_null, d_label, push_cnt, is_train);
+}
+
+int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                             const float* value, const float* label, int push_cnt, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_TRY(check_csr(h, nrows, offset));
+  if (nrows && !label) return h->fail(DFB_ERR_INVALID, "label is NULL");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
+  if (nnz && !ids) return h->fail(DFB_ERR_INVALID, "ids is NULL");
+  auto& in = h->in[h->seq & 1];
+  cudaStream_t cs = h->copy_stream;
+  if (h->seq >= 2) DFB_CUDA(h, cudaStreamWaitEvent(cs, in.consumed, 0));
+  DFB_TRY(h2d(h, in.off, offset, (nrows + 1) * sizeof(uint64_t), cs));
+  DFB_TRY(h2d(h, in.ids, ids, nnz * sizeof(uint64_t), cs));
+  if (value) DFB_TRY(h2d(h, in.val, value, nnz * sizeof(float), cs));
+  DFB_TRY(h2d(h, in.lab, label, nrows * sizeof(float), cs));
+  DFB_CUDA(h, cudaEventRecord(in.copied, cs));
+  DFB_CUDA(h, cudaStreamWaitEvent(h->stream, in.copied, 0));
+  int rc = step_raw_dev(h, nrows, nnz, in.off.as<uint64_t>(), in.ids.as<uint64_t>(),
+                        value ? in.val.as<float>() : nullptr, in.lab.as<float>(), push_cnt, is_train);
+  DFB_CUDA(h, cudaEventRecord(in.consumed, h->stream));
+  h->seq++;
+  if (rc != 0) return rc;
+  return snapshot_step(h);
+}
+
+int dfb_train_step_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids, const float* value,
+                       const float* label, int push_cnt, int is_train, dfb_progress* out, float* pred_out) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_TRY(dfb_train_step_raw_async(h, nrows, offset, ids, value, label, push_cnt, is_train));
+  if (pred_out && nrows)
+    DFB_CUDA(h, cudaMemcpyAsync(pred_out, h->pred.p, nrows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  return dfb_read_progress(h, out);
 }
 
 int dfb_train_step(dfb_handle h, size_t nrows, const uint64_t* offset, const uint32_t* index, const float* value,

@@ -172,6 +172,28 @@ int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset,
                          const uint64_t* keys, size_t nkeys, const float* cnt_or_null,
                          int is_train);
 
+/* ---------------------------------------------------------------------------------
+ * raw (un-localized) minibatches: Localizer::Compact on the device.
+ * dfb_localize is Localizer(max_index).Compact (src/data/localizer.h:41-51, localizer.cc:11-103)
+ * with host buffers in and out, bit-exact: index_out[nnz] = rank of every nnz's key, keys_out =
+ * ascending unique ReverseBytes(id % max_index), cnt_out = occurrence counts (may be NULL).
+ * dfb_train_step_raw* take the CSR<uint64> block the reader produced (BatchReader::Value) and run
+ * Localizer(-1).Compact + [kFeaCount push when push_cnt] + the fused step; the CSC view the
+ * gradient kernel needs falls out of the same radix sort.
+ * ------------------------------------------------------------------------------- */
+int dfb_localize(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* index,
+                 uint64_t max_index, uint32_t* index_out, uint64_t* keys_out, float* cnt_out,
+                 size_t* nkeys);
+int dfb_train_step_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                       const float* value_or_null, const float* label, int push_cnt, int is_train,
+                       dfb_progress* out, float* pred_out_or_null);
+int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                             const float* value_or_null, const float* label, int push_cnt,
+                             int is_train);
+int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset,
+                           const uint64_t* d_ids, const float* d_value_or_null, const float* d_label,
+                           int push_cnt, int is_train);
+
 /* blocks until the OLDEST not yet collected dfb_train_step_async step has finished and
  * returns that step's Progress (each async step snapshots its Progress into a pinned ring,
  * so collecting step t does not drain step t+1 from the pipeline). */
