@@ -263,8 +263,11 @@ def main_b200(args, rank, world, local_rank):
     U_mean = total_keys / nb
 
     cap = int(total_keys * 1.05) + 1024
+    extra = {}
+    if os.environ.get("DFB_L2_FETCH"):
+        extra["l2_fetch_granularity"] = int(os.environ["DFB_L2_FETCH"])
     E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap,
-                    overlap_auc=0 if args.no_overlap_auc else 1, **kw)
+                    overlap_auc=0 if args.no_overlap_auc else 1, **extra, **kw)
     ks = E.row_stride()
     devb = [dict(off=h["off"].to(dev), lab=h["lab"].to(dev), lidx=h["lidx"].to(dev), keys=h["keys"].to(dev),
                  cnt=h["cnt"].to(dev), U=h["U"]) for h in host]
@@ -454,7 +457,10 @@ def main_b200(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, {"unique_keys_per_batch": int(U_mean), "working_set_batches": nb,
                                          "table_keys": int(total_keys), "parallelism": "1 gpu, table resident in HBM"}),
-        "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_raw_ids": e2e_raw,
+        "roofline": roofline, "step_roofline": step_roof, "cpu_baseline": cpu,
+        # headline e2e = from the reader's raw uint64 CSR (Localizer::Compact inside the timed region, as in
+        # the reference arm's step); e2e_localized = the same with the batch localized beforehand
+        "e2e": e2e_raw if e2e_raw else e2e, "e2e_localized": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
         "stages_ms_per_step": {n: s["ms"] / max(s["count"], 1) for n, s in stages.items()},
         "loss_per_example": prog.loss / max(prog.nrows, 1), "datagen_s": t_gen,

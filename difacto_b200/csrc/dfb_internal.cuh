@@ -65,6 +65,9 @@ struct FmView {
   // w = wbase[w_pos ? w_pos[u] : u]; w_pos[u] == -1 -> 0
   const float* wbase;
   const int* w_pos;
+  // optional packed pulled view {bits(w), vrow} per key: one 8-byte load per nnz instead of two
+  // 4-byte loads from different arrays (fast kernel only; overrides wbase/w_pos/v_pos when set)
+  const int2* wv;
   // V row = vbase + (int64)r * vstride, r = v_pos[u] (or u when dense && v_pos[u] >= 0); -1 -> absent
   const float* vbase;
   const int* v_pos;
@@ -126,7 +129,7 @@ int launch_table_init(Table& t, unsigned seed, cudaStream_t s);
 // find (or insert) keys; slot_out[i] = hash position or -1.  When pull outputs are non-null also
 // emits w and vrow of each entry.
 int launch_lookup(Table& t, const uint64_t* keys, size_t n, bool insert, int* slot_out,
-                  float* w_out, int* vrow_out, cudaStream_t s);
+                  float* w_out, int* vrow_out, int2* wv_out, cudaStream_t s);
 // SGDUpdater::Update(kFeaCount) incl. the InitV pass.  flags/pos/cub_tmp are workspaces of n ints.
 int launch_feacnt(Table& t, const Params& p, const int* slot, size_t n, const float* cnt,
                   int* flags, int* pos, void* cub_tmp, size_t cub_bytes, cudaStream_t s);
@@ -158,7 +161,7 @@ int launch_update_ragged(Table& t, const Params& p, const int* slot, size_t n, c
 int launch_penalty(const Params& p, DevProgress* prog, const float* w_arr, const int* vrow,
                    const float* V, int ks, int dense, size_t n, cudaStream_t s);
 int launch_pull_view(Table& t, const int* slot, size_t n, float* w_out, int* vrow_out,
-                     cudaStream_t s);
+                     int2* wv_out, cudaStream_t s);
 int launch_lens_scan(const int* lens, size_t n, int* pos, void* cub_tmp, size_t cub_bytes,
                      cudaStream_t s);
 // Loss::Evaluate / BinClassMetric::AUC on device; results added to prog (or written to out)

@@ -47,6 +47,7 @@ struct dfb_engine {
   uint64_t launches = 0;
 
   // workspaces (grown on demand)
+  DevBuf u_wv;
   DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
   DevBuf auc_k, auc_v, auc_tmp;
   DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
@@ -58,9 +59,9 @@ struct dfb_engine {
   struct InSet { DevBuf off, idx, val, lab, keys, cnt, ids; cudaEvent_t copied = nullptr, consumed = nullptr; } in[2];
   uint64_t seq = 0;
   // per-step Progress snapshots of the pipelined path (pinned ring + completion events)
-  static constexpr int kRing = 4;
+  static constexpr int kRing = 8;
   DevProgress* h_ring = nullptr;
-  cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t submitted = 0, collected = 0;
   DevProgress backlog;             // snapshots folded in when the ring was full
   // optional per-stage CUDA-event timing (bench.py's roofline numbers)
@@ -191,6 +192,7 @@ int ensure_key_ws(dfb_engine* h, size_t n) {
   DFB_TRY(h->ensure(h->slot, n * sizeof(int)));
   DFB_TRY(h->ensure(h->u_w, n * sizeof(float)));
   DFB_TRY(h->ensure(h->u_vrow, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->u_wv, n * sizeof(int2)));
   DFB_TRY(h->ensure(h->flags, n * sizeof(int)));
   DFB_TRY(h->ensure(h->pos, n * sizeof(int)));
   DFB_TRY(h->ensure(h->cub, scan_tmp_bytes(n)));
@@ -279,16 +281,17 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   {
   StageTimer tm(h, 0);
   if (d_cnt) {
-    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, nullptr, nullptr, s);
+    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, nullptr, nullptr, nullptr, s);
     h->launches += launch_feacnt(h->tab, h->prm, slot, U, d_cnt, flags, pos, h->cub.p, h->cub.bytes, s);
-    h->launches += launch_pull_view(h->tab, slot, U, u_w, u_vrow, s);
+    h->launches += launch_pull_view(h->tab, slot, U, u_w, u_vrow, h->u_wv.as<int2>(), s);
   } else {
-    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, u_w, u_vrow, s);
+    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, u_w, u_vrow, h->u_wv.as<int2>(), s);
   }
   }
   FmView v;
   memset(&v, 0, sizeof(v));
   v.wbase = u_w; v.w_pos = nullptr;
+  v.wv = h->u_wv.as<int2>();
   v.vbase = h->tab.V; v.v_pos = u_vrow; v.vstride = h->tab.rs; v.dense = 0;
   if (sorted) {
     DFB_TRY(ensure_sorted_ws(h, nrows, nnz, U, d_val != nullptr));
@@ -470,6 +473,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   p.l1 = 1.f; p.l2 = 0.f; p.V_l2 = .01f; p.lr = .01f; p.lr_beta = 1.f; p.V_lr = .01f; p.V_lr_beta = 1.f;
   p.V_init_scale = .01f; p.V_threshold = 10; p.V_dim = -1; p.seed = 0;
   long long table_capacity = 1 << 20, v_capacity = -1;
+  int l2_fetch = 0;
   struct FR { const char* name; float* dst; float lo, hi; };
   FR fr[] = {{"l1", &p.l1, 0, 1e10f}, {"l2", &p.l2, 0, 1e10f}, {"V_l2", &p.V_l2, 0, 1e10f},
              {"lr", &p.lr, 0, 10}, {"lr_beta", &p.lr_beta, 0, 1e10f}, {"V_lr", &p.V_lr, 0, 1e10f},
@@ -506,6 +510,10 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     else if (k == "V_capacity") { if (!need_int(0, 1LL << 30)) { delete h; return DFB_ERR_PARAM; } v_capacity = x; }
     else if (k == "compute_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->compute_auc = (int)x; }
     else if (k == "force_generic") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->force_generic = (int)x; }
+    else if (k == "l2_fetch_granularity") {
+      if (!need_int(32, 128)) { delete h; return DFB_ERR_PARAM; }
+      l2_fetch = (int)x;
+    }
     else if (k == "overlap_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->overlap_auc = (int)x; }
     else if (k == "scatter") {
       if (v == "sorted") h->scatter_sorted = 1;
@@ -525,6 +533,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     return (int)DFB_ERR_CUDA;
   };
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) return cfail("cudaSetDevice");
+  if (l2_fetch) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)l2_fetch);   // a hint; errors ignored
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
@@ -571,7 +580,7 @@ int dfb_destroy(dfb_handle h) {
   if (!h) return DFB_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->l_rkeys, &h->l_skeys, &h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow, &h->l_keys,
+  DevBuf* bufs[] = {&h->u_wv, &h->l_rkeys, &h->l_skeys, &h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow, &h->l_keys,
                     &h->l_lidx, &h->l_cnt, &h->l_scal, &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
                     &h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
                     &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
@@ -655,7 +664,7 @@ int dfb_push_feacnt(dfb_handle h, const uint64_t* keys, size_t n, const float* c
   DFB_TRY(h2d(h, h->keys, keys, n * sizeof(uint64_t), s));
   DFB_TRY(h2d(h, h->cnt, cnt, n * sizeof(float), s));
   DFB_TRY(ensure_key_ws(h, n));
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, h->cnt.as<float>(), h->flags.as<int>(),
                                h->pos.as<int>(), h->cub.p, h->cub.bytes, s);
   return sync_and_check(h);
@@ -677,7 +686,7 @@ int dfb_pull(dfb_handle h, const uint64_t* keys, size_t n, float* vals_out, size
   if (k == 0) {
     if (vals_cap < n) return h->fail(DFB_ERR_INVALID, "vals_out too small");
     h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), h->u_w.as<float>(),
-                                 h->u_vrow.as<int>(), s);
+                                 h->u_vrow.as<int>(), nullptr, s);
     DFB_CUDA(h, cudaMemcpyAsync(vals_out, h->u_w.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     DFB_TRY(sync_and_check(h));
     *nvals = n; *nlens = 0;   // lens->resize(V_dim == 0 ? 0 : size), sgd_updater.cc:40
@@ -689,7 +698,7 @@ int dfb_pull(dfb_handle h, const uint64_t* keys, size_t n, float* vals_out, size
   DFB_TRY(h->ensure(h->lens, n * sizeof(int)));
   DFB_TRY(h->ensure(h->vals, n * (size_t)(k + 1) * sizeof(float)));
   DFB_TRY(h->ensure(h->nvals, sizeof(unsigned long long)));
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_pack_ragged(h->tab, h->prm, h->slot.as<int>(), n, h->lens.as<int>(), h->pos.as<int>(),
                                     h->vals.as<float>(), h->nvals.as<unsigned long long>(), h->cub.p,
                                     h->cub.bytes, s);
@@ -733,7 +742,7 @@ int dfb_push_grad(dfb_handle h, const uint64_t* keys, size_t n, const float* gra
     d_lens = h->lens.as<int>();
     h->launches += launch_lens_scan(d_lens, n, h->pos.as<int>(), h->cub.p, h->cub.bytes, s);
   }
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_update_ragged(h->tab, h->prm, h->slot.as<int>(), n, h->vals.as<float>(), d_lens,
                                       h->pos.as<int>(), h->flags.as<int>(), s);
   h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, h->flags.as<int>(), h->pos.as<int>(),
@@ -1077,7 +1086,7 @@ int dfb_read_entries(dfb_handle h, const uint64_t* keys, size_t n, float* scal_o
   DFB_TRY(h->ensure(h->rcg, n * (size_t)(k ? k : 1) * sizeof(float)));
   DFB_CUDA(h, cudaMemsetAsync(h->rV.p, 0, n * (size_t)(k ? k : 1) * sizeof(float), s));
   DFB_CUDA(h, cudaMemsetAsync(h->rcg.p, 0, n * (size_t)(k ? k : 1) * sizeof(float), s));
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, false, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, false, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_read_entries(h->tab, h->slot.as<int>(), n, h->scal.as<float>(), h->hasv.as<int>(),
                                      h->rV.as<float>(), h->rcg.as<float>(), k, s);
   DFB_CUDA(h, cudaMemcpyAsync(scal_out, h->scal.p, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1122,7 +1131,7 @@ int dfb_dev_feacnt(dfb_handle h, const uint64_t* d_keys, size_t n, const float* 
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
-  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, d_cnt, h->flags.as<int>(), h->pos.as<int>(),
                                h->cub.p, h->cub.bytes, s);
   DFB_CUDA(h, cudaGetLastError());
@@ -1136,7 +1145,7 @@ static int dev_pull_rows_impl(dfb_handle h, const uint64_t* d_keys, size_t n, fl
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
-  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_gather_rows(h->tab, h->slot.as<int>(), n, d_w_out, d_hasv_out, d_hasv_out2,
                                     h->prm.V_dim > 0 ? d_V_out : nullptr, s);
   DFB_CUDA(h, cudaGetLastError());
@@ -1300,7 +1309,7 @@ int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const floa
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
-  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   int nl = h->force_generic ? -1 : launch_update_pushed(h->tab, h->prm, h->slot.as<int>(), d_hasv, n, d_gw, d_gV,
                                                         h->flags.as<int>(), s);
   if (nl < 0)

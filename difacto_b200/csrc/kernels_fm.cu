@@ -106,10 +106,16 @@ __global__ void __launch_bounds__(256) k_fm_fast(FmBatch b, FmView v) {
       if (valid) {
         u = __ldg(b.index + j);
         x = HAS_VAL ? __ldg(b.value + j) : 1.f;
-        const int wp = v.w_pos ? __ldg(v.w_pos + u) : (int)u;
-        w = wp >= 0 ? __ldg(v.wbase + wp) : 0.f;
-        vr = __ldg(v.v_pos + u);
-        if (v.dense && vr >= 0) vr = (int)u;
+        if (v.wv) {
+          const int2 t = __ldg(v.wv + u);
+          w = __int_as_float(t.x);
+          vr = t.y;
+        } else {
+          const int wp = v.w_pos ? __ldg(v.w_pos + u) : (int)u;
+          w = wp >= 0 ? __ldg(v.wbase + wp) : 0.f;
+          vr = __ldg(v.v_pos + u);
+          if (v.dense && vr >= 0) vr = (int)u;
+        }
         if (MODE == 2 && b.occ_row != nullptr) {   // nullptr: the CSC view already exists (GPU localizer)
           if (HAS_VAL) b.occ_rowx[j] = ((unsigned long long)row << 32) | (unsigned long long)__float_as_uint(x);
           else b.occ_row[j] = (uint32_t)row;

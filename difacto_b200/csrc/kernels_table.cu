@@ -58,7 +58,7 @@ __global__ void k_table_init(Entry* tab, uint64_t cap, TableState* st, DevProgre
 // model_[key] (sgd_updater.cc:43-45,65-67,86-88): find or default-construct
 template <bool INSERT>
 __global__ void k_lookup(Table t, const uint64_t* __restrict__ keys, size_t n, int* __restrict__ slot_out,
-                         float* __restrict__ w_out, int* __restrict__ vrow_out) {
+                         float* __restrict__ w_out, int* __restrict__ vrow_out, int2* __restrict__ wv_out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long key = keys[i];
@@ -97,6 +97,7 @@ __global__ void k_lookup(Table t, const uint64_t* __restrict__ keys, size_t n, i
     }
     w_out[i] = w;
     vrow_out[i] = vr;
+    if (wv_out) wv_out[i] = make_int2(__float_as_int(w), vr);
   }
 }
 
@@ -383,12 +384,15 @@ __global__ void __launch_bounds__(256) k_penalty(Params p, DevProgress* prog, co
 
 // w and vrow of already-located entries (the Pull of the fused path after a feature-count push)
 __global__ void k_pull_view(Table t, const int* __restrict__ slot, size_t n, float* __restrict__ w_out,
-                            int* __restrict__ vrow_out) {
+                            int* __restrict__ vrow_out, int2* __restrict__ wv_out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = slot[i];
-  w_out[i] = s >= 0 ? t.tab[s].w : 0.f;
-  vrow_out[i] = s >= 0 ? t.tab[s].vrow : -1;
+  const float w = s >= 0 ? t.tab[s].w : 0.f;
+  const int vr = s >= 0 ? t.tab[s].vrow : -1;
+  w_out[i] = w;
+  vrow_out[i] = vr;
+  if (wv_out) wv_out[i] = make_int2(__float_as_int(w), vr);
 }
 
 // SGDUpdater::Get: lens (sgd_updater.cc:46-53)
@@ -749,12 +753,12 @@ int launch_table_init(Table& t, unsigned seed, cudaStream_t s) {
 }
 
 int launch_lookup(Table& t, const uint64_t* keys, size_t n, bool insert, int* slot_out, float* w_out,
-                  int* vrow_out, cudaStream_t s) {
+                  int* vrow_out, int2* wv_out, cudaStream_t s) {
   if (n == 0) return 0;
   const int threads = 256;
   const int grid = (int)((n + threads - 1) / threads);
-  if (insert) k_lookup<true><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out);
-  else        k_lookup<false><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out);
+  if (insert) k_lookup<true><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out, wv_out);
+  else        k_lookup<false><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out, wv_out);
   return 1;
 }
 
@@ -845,9 +849,10 @@ int launch_penalty(const Params& p, DevProgress* prog, const float* w_arr, const
   return 1;
 }
 
-int launch_pull_view(Table& t, const int* slot, size_t n, float* w_out, int* vrow_out, cudaStream_t s) {
+int launch_pull_view(Table& t, const int* slot, size_t n, float* w_out, int* vrow_out, int2* wv_out,
+                     cudaStream_t s) {
   if (n == 0) return 0;
-  k_pull_view<<<(int)((n + 255) / 256), 256, 0, s>>>(t, slot, n, w_out, vrow_out);
+  k_pull_view<<<(int)((n + 255) / 256), 256, 0, s>>>(t, slot, n, w_out, vrow_out, wv_out);
   return 1;
 }
 

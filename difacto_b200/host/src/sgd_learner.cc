@@ -171,14 +171,24 @@ void SGDLearner::IterateData(const sgd::Job& job, sgd::Progress* progress) {
                      train ? static_cast<unsigned>(param_.batch_size) * static_cast<unsigned>(param_.shuffle) : 0u,
                      train ? param_.neg_sampling : 1.0f);
   while (reader.Next()) {
+    const bool push_cnt = train && job.epoch == 0;   // :201-202
+    if (param_.fused) {
+      // Localizer::Compact + [kFeaCount push] + Pull/Predict/.../Push in one device call on the raw block
+      const auto blk = reader.Value();
+      const auto& eng = GetUpdater()->engine();
+      dfb_progress pr;
+      eng->Check(dfb_train_step_raw(eng->handle(), blk.size, reinterpret_cast<const uint64_t*>(blk.offset),
+                                    blk.index, blk.value, blk.label, push_cnt ? 1 : 0, train ? 1 : 0, &pr, nullptr),
+                 "dfb_train_step_raw");
+      progress->loss += pr.loss; progress->penalty += pr.penalty; progress->auc += pr.auc; progress->nrows += pr.nrows;
+      continue;
+    }
     RowBlockContainer<unsigned> data;
     std::vector<feaid_t> feaids;
     std::vector<real_t> feacnt;
-    const bool push_cnt = train && job.epoch == 0;   // :201-202
     Localizer lc(-1, 2);
     lc.Compact(reader.Value(), &data, &feaids, push_cnt ? &feacnt : nullptr);
-    if (param_.fused) BatchFused(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
-    else BatchPluginCalls(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
+    BatchPluginCalls(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
   }
 }
 

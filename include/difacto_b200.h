@@ -196,7 +196,8 @@ int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_
 
 /* blocks until the OLDEST not yet collected dfb_train_step_async step has finished and
  * returns that step's Progress (each async step snapshots its Progress into a pinned ring,
- * so collecting step t does not drain step t+1 from the pipeline). */
+ * so collecting step t does not drain step t+1 from the pipeline).  Up to 8 steps may be outstanding;
+ * beyond that the oldest snapshots are folded into the sum dfb_read_progress returns. */
 int dfb_wait_step(dfb_handle h, dfb_progress* out);
 
 /* per-stage device timing with CUDA events on the handle's stream (bench.py's roofline):

@@ -66,6 +66,7 @@ def test_raw_step_equals_localized_step_and_oracle(V_dim, valued, scatter):
     kw = dict(V_dim=V_dim, l1=0.2, l2=0.01, lr=0.2, V_lr=0.05, V_threshold=3, V_l2=0.02, V_init_scale=0.2, seed=5)
     batches = [rand_batch(rng, 150, 30, 400, valued and j % 2 == 0) for j in range(4)]
     M = O.Oracle(**kw)
+    exact = scatter == "sorted" and V_dim in (8, 16, 32, 64, 128)    # the atomic-free path is bit-reproducible
     R = capi.Engine(table_capacity=1 << 14, scatter=scatter, **kw)     # raw ids -> GPU localizer
     L = capi.Engine(table_capacity=1 << 14, scatter=scatter, **kw)     # host-localized
     for ep in range(3):
@@ -77,11 +78,11 @@ def test_raw_step_equals_localized_step_and_oracle(V_dim, valued, scatter):
             assert pr.nrows == ref[4]
             assert abs(pr.loss - ref[0]) <= 1e-4 * abs(ref[0]) + 1e-4
             assert abs(pr.penalty - ref[1]) <= 1e-4 * abs(ref[1]) + 1e-5
-            if scatter == "sorted":
+            if exact:
                 assert pr.loss == pl.loss and pr.penalty == pl.penalty     # same kernels, same CSC order
     keys = np.unique(np.concatenate([O.reverse_bytes_np(b[2]) for b in batches]))
     sr, sl = R.read_entries(keys), L.read_entries(keys)
-    if scatter == "sorted":
+    if exact:
         for a, b in zip(sr, sl):
             assert np.array_equal(a, b)        # bit-identical to the host-localized path
     oscal, ohasv, oV, ocg = oracle_state(M, keys)
