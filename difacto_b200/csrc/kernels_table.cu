@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
   constexpr int G = 32 / LPR;
   constexpr int NPASS = 32 / G;
   constexpr int UNRB = NPASS >= 2 ? 2 : 1;
+  constexpr int kHeavy = 64;     // occurrence-list length above which a key is reduced cooperatively
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -618,13 +619,46 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
     float gw = 0.f, xxp = 0.f, x0 = 0.f;
     uint32_t row0 = 0;
     if (SRC == 1 && active) gw = p_row[i];      // dense source: p_row aliases gw_in
-    for (int o = o0; o < o1; ++o) {
-      uint32_t row; float x;
-      load_occ<HAS_VAL>(occ, o, row, x);
-      const float pr = __ldg(p_row + row);
-      gw = __fadd_rn(gw, __fmul_rn(pr, x));                        // spmv.h:162-164
-      if (HAS_VAL) xxp = __fadd_rn(xxp, __fmul_rn(pr, __fmul_rn(x, x)));
-      if (o == o0) { row0 = row; x0 = x; }
+    // keys with at most kHeavy occurrences: this lane sums them strictly in row order (the
+    // reference's order, spmv.h:162-164), four loads in flight; longer lists ("hot" features of a
+    // skewed batch) are reduced by the whole warp below (fixed tree: still bit-reproducible)
+    const bool heavy = (o1 - o0) > kHeavy;
+    if (o0 < o1) load_occ<HAS_VAL>(occ, o0, row0, x0);
+    if (!heavy) {
+      for (int o = o0; o < o1; o += 4) {
+        uint32_t rw[4]; float xs[4], pr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          rw[q] = 0; xs[q] = 0.f; pr[q] = 0.f;
+          if (o + q < o1) { load_occ<HAS_VAL>(occ, o + q, rw[q], xs[q]); pr[q] = __ldg(p_row + rw[q]); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (o + q < o1) {
+            gw = __fadd_rn(gw, __fmul_rn(pr[q], xs[q]));
+            if (HAS_VAL) xxp = __fadd_rn(xxp, __fmul_rn(pr[q], __fmul_rn(xs[q], xs[q])));
+          }
+        }
+      }
+    }
+    if (SRC == 0) {
+      unsigned hm = __ballot_sync(kFull, heavy);
+      while (hm) {
+        const int hl = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const int ho0 = __shfl_sync(kFull, o0, hl), ho1 = __shfl_sync(kFull, o1, hl);
+        float a = 0.f, b2 = 0.f;
+        for (int o = ho0 + lane; o < ho1; o += 32) {
+          uint32_t row; float x;
+          load_occ<HAS_VAL>(occ, o, row, x);
+          const float pr = __ldg(p_row + row);
+          a = fmaf(pr, x, a);
+          if (HAS_VAL) b2 = fmaf(pr, x * x, b2);
+        }
+        a = warp_sum(a);
+        if (HAS_VAL) b2 = warp_sum(b2);
+        if (lane == hl) { gw = a; xxp = b2; }
+      }
     }
     if (!HAS_VAL) xxp = gw;
     if (SRC == 1) xxp = 0.f;                    // pushed rows are complete gradients
@@ -665,6 +699,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
         const uint32_t r0 = __shfl_sync(kFull, row0, kk);
         const float xx0 = __shfl_sync(kFull, x0, kk);
         v[q] = c[q] = g[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o1k[q] - o0k[q] > kHeavy) vrk[q] = -1;      // handled by the whole warp after the passes
         if (vrk[q] >= 0) {
           if (APPLY) {
             const float* Vr = t.V + (size_t)vrk[q] * t.rs + sub * 4;
@@ -688,12 +723,24 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
 #pragma unroll
       for (int q = 0; q < UNRB; ++q) {
         if (vrk[q] < 0) continue;
-        for (int o = o0k[q] + 1; o < o1k[q]; ++o) {     // further occurrences, still in row order
-          uint32_t row; float x;
-          load_occ<HAS_VAL>(occ, o, row, x);
-          const float4 tt = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)row * K + sub * 4));
-          g[q].x = __fadd_rn(g[q].x, __fmul_rn(tt.x, x)); g[q].y = __fadd_rn(g[q].y, __fmul_rn(tt.y, x));
-          g[q].z = __fadd_rn(g[q].z, __fmul_rn(tt.z, x)); g[q].w = __fadd_rn(g[q].w, __fmul_rn(tt.w, x));
+        for (int o = o0k[q] + 1; o < o1k[q]; o += 4) {   // further occurrences: loads 4 ahead, sums in row order
+          float4 tt[4]; float xs[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            xs[r] = 0.f; tt[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o + r < o1k[q]) {
+              uint32_t row;
+              load_occ<HAS_VAL>(occ, o + r, row, xs[r]);
+              tt[r] = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)row * K + sub * 4));
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            if (o + r < o1k[q]) {
+              g[q].x = __fadd_rn(g[q].x, __fmul_rn(tt[r].x, xs[r])); g[q].y = __fadd_rn(g[q].y, __fmul_rn(tt[r].y, xs[r]));
+              g[q].z = __fadd_rn(g[q].z, __fmul_rn(tt[r].z, xs[r])); g[q].w = __fadd_rn(g[q].w, __fmul_rn(tt[r].w, xs[r]));
+            }
+          }
         }
         if (APPLY) {
           if (acc_pen) pen += 0.5f * p.V_l2 * (v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w);
@@ -718,6 +765,77 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
           *reinterpret_cast<float4*>(grow + sub * 4) =
               make_float4(__fsub_rn(g[q].x, __fmul_rn(v[q].x, xp)), __fsub_rn(g[q].y, __fmul_rn(v[q].y, xp)),
                           __fsub_rn(g[q].z, __fmul_rn(v[q].z, xp)), __fsub_rn(g[q].w, __fmul_rn(v[q].w, xp)));
+        }
+      }
+    }
+    // ---------------- hot keys: the whole warp reduces one occurrence list ----------------
+    if (SRC == 0) {
+      unsigned hm = __ballot_sync(kFull, active && (o1 - o0) > kHeavy && vr >= 0);
+      while (hm) {
+        const int hl = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const int hvr = __shfl_sync(kFull, vr, hl);
+        const int ho0 = __shfl_sync(kFull, o0, hl), ho1 = __shfl_sync(kFull, o1, hl);
+        const float hxp = __shfl_sync(kFull, xxp, hl);
+        const size_t ik = base + (size_t)hl;
+        float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), hc = hv;
+        float* Vr = nullptr;
+        if (grp == 0) {
+          if (APPLY) {
+            Vr = t.V + (size_t)hvr * t.rs + sub * 4;
+            hv = *reinterpret_cast<const float4*>(Vr);
+            hc = *reinterpret_cast<const float4*>(Vr + t.ks);
+          } else {
+            hv = __ldg(reinterpret_cast<const float4*>(V_pulled + ik * (size_t)K + sub * 4));
+          }
+        }
+        float4 acc[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = ho0 + grp; o < ho1; o += 4 * G) {    // G row-groups x 4 rows in flight
+          float4 tt[4]; float xs[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            xs[r] = 0.f; tt[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o + r * G < ho1) {
+              uint32_t row;
+              load_occ<HAS_VAL>(occ, o + r * G, row, xs[r]);
+              tt[r] = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)row * K + sub * 4));
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            acc[r].x = fmaf(tt[r].x, xs[r], acc[r].x); acc[r].y = fmaf(tt[r].y, xs[r], acc[r].y);
+            acc[r].z = fmaf(tt[r].z, xs[r], acc[r].z); acc[r].w = fmaf(tt[r].w, xs[r], acc[r].w);
+          }
+        }
+        float4 hg = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                                (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+          hg.x += __shfl_xor_sync(kFull, hg.x, o); hg.y += __shfl_xor_sync(kFull, hg.y, o);
+          hg.z += __shfl_xor_sync(kFull, hg.z, o); hg.w += __shfl_xor_sync(kFull, hg.w, o);
+        }
+        if (grp == 0) {
+          if (acc_pen) pen += 0.5f * p.V_l2 * (hv.x * hv.x + hv.y * hv.y + hv.z * hv.z + hv.w * hv.w);
+          if (APPLY) {
+            adagrad_step(p, __fsub_rn(hg.x, __fmul_rn(hv.x, hxp)), hv.x, hc.x);
+            adagrad_step(p, __fsub_rn(hg.y, __fmul_rn(hv.y, hxp)), hv.y, hc.y);
+            adagrad_step(p, __fsub_rn(hg.z, __fmul_rn(hv.z, hxp)), hv.z, hc.z);
+            adagrad_step(p, __fsub_rn(hg.w, __fmul_rn(hv.w, hxp)), hv.w, hc.w);
+            *reinterpret_cast<float4*>(Vr) = hv;
+            *reinterpret_cast<float4*>(Vr + t.ks) = hc;
+          } else {
+            float* grow = gV_out + ik * (size_t)K;
+            if (seg.nseg != 0) {
+              int sg = 0;
+              while (sg + 1 < seg.nseg && (int)ik >= seg.bounds[sg + 1]) ++sg;
+              grow = seg.gV[sg] + (ik - (size_t)seg.bounds[sg]) * (size_t)K;
+            }
+            *reinterpret_cast<float4*>(grow + sub * 4) =
+                make_float4(__fsub_rn(hg.x, __fmul_rn(hv.x, hxp)), __fsub_rn(hg.y, __fmul_rn(hv.y, hxp)),
+                            __fsub_rn(hg.z, __fmul_rn(hv.z, hxp)), __fsub_rn(hg.w, __fmul_rn(hv.w, hxp)));
+          }
         }
       }
     }

@@ -279,6 +279,27 @@ def test_fused_trajectory_vs_oracle(V_dim, valued, force_generic, scatter):
         assert (ohasv == 1).sum() > 10
 
 
+@pytest.mark.parametrize("V_dim,valued", [(16, True), (64, False), (128, True)])
+def test_hot_keys_vs_oracle(V_dim, valued):
+    # a skewed batch: 25 features shared by 700 rows -> ~400 occurrences per key, far above the
+    # threshold at which a key's gradient is reduced by a whole warp instead of one lane group
+    rng = np.random.default_rng(4242 + V_dim)
+    kw = dict(V_dim=V_dim, l1=0.01, l2=0.01, lr=0.05, V_lr=0.02, V_threshold=0, V_l2=0.02, V_init_scale=0.1, seed=8)
+    batches = [rand_batch(rng, 700, 30, 25, valued, min_nnz=5) for _ in range(3)]
+    # plus a few cold keys so that short and long lists share warps
+    for b in batches:
+        b[2][::17] = rng.integers(10 ** 6, 10 ** 7, len(b[2][::17])).astype(np.uint64)
+    M, E = run_both(kw, batches, epochs=3, val_every=0)
+    keys = np.unique(np.concatenate([O.reverse_bytes_np(b[2]) for b in batches]))
+    compare_state(M, E, keys, tol=dict(rtol=2e-3, atol=2e-5))
+    R = engine(**kw)
+    for ep in range(3):
+        for (o, l, i, v) in batches:
+            R.train_step_raw(o, i, v, l, push_cnt=(ep == 0), is_train=True)
+    for a, b in zip(R.read_entries(keys), E.read_entries(keys)):
+        assert np.array_equal(a, b)        # GPU-localized and host-localized paths are bit-identical
+
+
 def test_edge_cases_empty_rows_and_batches():
     kw = dict(V_dim=8, l1=0.0, l2=0.0, lr=0.1, V_threshold=0, seed=1)
     M, E = O.Oracle(**kw), engine(**kw)
