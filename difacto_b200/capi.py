@@ -89,7 +89,7 @@ def lib():
         L.dfb_peer_close.argtypes = [vp, vp]
         L.dfb_peer_free.argtypes = [vp, vp]
         L.dfb_dev_pull_rows_peer.argtypes = [vp, vp, sz, vp, vp, vp, vp]
-        L.dfb_dev_fm_step_peer.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp, vp]
+        L.dfb_dev_fm_step_peer.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int]
         L.dfb_localize.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, C.POINTER(sz)]
         L.dfb_train_step_raw.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Progress), vp]
         L.dfb_train_step_raw_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
@@ -359,13 +359,13 @@ class Engine:
                                                _p(d_hasv_local)))
 
     def dev_fm_step_peer(self, nrows, nnz, d_off, d_idx, d_val, d_lab, nkeys, d_w, d_hasv, d_V, seg_bounds, peer_gw,
-                         peer_gV):
+                         peer_gV, first_seg=0):
         nseg = len(peer_gw)
         sb = (C.c_size_t * (nseg + 1))(*[int(x) for x in seg_bounds])
         gw = (C.c_void_p * nseg)(*[int(x) for x in peer_gw])
         gV = (C.c_void_p * nseg)(*[int(x) for x in peer_gV])
         self._ck(self.L.dfb_dev_fm_step_peer(self.h, nrows, nnz, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys,
-                                             _p(d_w), _p(d_hasv), _p(d_V), nseg, sb, gw, gV))
+                                             _p(d_w), _p(d_hasv), _p(d_V), nseg, sb, gw, gV, int(first_seg)))
 
     def dev_push_rows(self, d_keys, n, d_gw, d_hasv, d_gV):
         self._ck(self.L.dfb_dev_push_rows(self.h, _p(d_keys), n, _p(d_gw), _p(d_hasv), _p(d_gV)))

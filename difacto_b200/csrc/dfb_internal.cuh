@@ -87,6 +87,7 @@ struct FmView {
 // sorted key list, straight into that owner's receive buffer over NVLink (peer pointers)
 struct SegDst {
   int nseg;
+  int rot;            // first key (multiple of 32) this rank starts with: staggers the peers' inbound traffic
   int bounds[9];      // key index boundaries of the segments (nseg + 1 used)
   float* gw[8];       // per segment: destination of gw for the segment's first key
   float* gV[8];       // per segment: destination row of gV for the segment's first key

@@ -1213,7 +1213,7 @@ int dfb_dev_fm_step(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_of
 int dfb_dev_fm_step_peer(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint32_t* d_index,
                          const float* d_value, const float* d_label, size_t nkeys, const float* d_w,
                          const int* d_hasv, const float* d_V, int nseg, const size_t* seg_bounds,
-                         float* const* peer_gw, float* const* peer_gV) {
+                         float* const* peer_gw, float* const* peer_gV, int first_seg) {
   if (!h) return DFB_ERR_INVALID;
   if (nseg < 1 || nseg > 8 || !seg_bounds || !peer_gw || !peer_gV)
     return h->fail(DFB_ERR_INVALID, "dfb_dev_fm_step_peer: 1..8 segments with destinations required");
@@ -1222,6 +1222,7 @@ int dfb_dev_fm_step_peer(dfb_handle h, size_t nrows, size_t nnz, const uint64_t*
   sd.nseg = nseg;
   for (int i = 0; i <= nseg; ++i) sd.bounds[i] = (int)seg_bounds[i];
   for (int i = 0; i < nseg; ++i) { sd.gw[i] = peer_gw[i]; sd.gV[i] = peer_gV[i]; }
+  if (first_seg >= 0 && first_seg < nseg) sd.rot = sd.bounds[first_seg] / 32 * 32;
   if ((size_t)sd.bounds[nseg] != nkeys) return h->fail(DFB_ERR_INVALID, "seg_bounds[nseg] must equal nkeys");
   const int k = h->prm.V_dim;
   if (!(h->scatter_sorted && !h->force_generic && fm_fast_supported(k) && h->tab.ks == k))

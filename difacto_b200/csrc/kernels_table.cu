@@ -600,7 +600,12 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   float pen = 0.f;
-  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+  const size_t npad = (n + 31) / 32 * 32;
+  for (size_t b0 = warp0 * 32; b0 < n; b0 += nwarps * 32) {
+    // start at this rank's own key segment and go round: at any moment the ranks of a sharded
+    // step store into different peers (seg.rot == 0 outside the peer-store path)
+    size_t base = b0 + (size_t)seg.rot;
+    if (base >= npad) base -= npad;
     // ---------------- phase A: one key per lane ----------------
     const size_t i = base + lane;
     const bool active = i < n;

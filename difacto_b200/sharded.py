@@ -262,7 +262,8 @@ class PeerShardedStore(ShardedStore):
             for src in range(S):
                 self.b.feacnt(keys_r[seg[src]:seg[src + 1]], cnt_r[seg[src]:seg[src + 1]])
         # ---- Pull: gather + store into the requester's buffer (its key order = owner order) ----
-        for src in range(S):
+        for ph in range(S):       # ring order: in phase ph every rank stores into a different peer
+            src = (me + ph) % S
             n = recv[src]
             if n == 0:
                 continue
@@ -288,7 +289,7 @@ class PeerShardedStore(ShardedStore):
             pgw.append(self.push_peer[s] + off * 4)
             pgV.append(self.push_peer[s] + self.off_gV + off * ks * 4)
         E.dev_fm_step_peer(batch["nrows"], batch["nnz"], batch["off"], batch["lidx"], batch.get("val"), batch["lab"], U,
-                           w, hasv, V, bounds, pgw, pgV)
+                           w, hasv, V, bounds, pgw, pgV, first_seg=me)
         self._barrier()
         self._mark("worker_fm_store")
         # ---- Push(kGradient): one Update per worker, rank order ----

@@ -269,7 +269,8 @@ int dfb_dev_pull_rows_peer(dfb_handle h, const uint64_t* d_keys, size_t n, float
 int dfb_dev_fm_step_peer(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset,
                          const uint32_t* d_index, const float* d_value_or_null, const float* d_label,
                          size_t nkeys, const float* d_w, const int* d_hasv, const float* d_V, int nseg,
-                         const size_t* seg_bounds, float* const* peer_gw, float* const* peer_gV);
+                         const size_t* seg_bounds, float* const* peer_gw, float* const* peer_gV,
+                         int first_seg /* segment to start with (own rank): staggers peer traffic */);
 
 /* the CUDA stream (cudaStream_t) the handle enqueues on, for event interop with torch */
 void* dfb_stream(dfb_handle h);
