@@ -34,7 +34,7 @@ EXPORTS = [
     "dfb_wait_step", "dfb_profile", "dfb_profile_read",
     "dfb_peer_alloc", "dfb_peer_open", "dfb_peer_close", "dfb_peer_free", "dfb_dev_pull_rows_peer",
     "dfb_dev_fm_step_peer", "dfb_localize", "dfb_train_step_raw", "dfb_train_step_raw_async",
-    "dfb_train_step_raw_dev",
+    "dfb_train_step_raw_dev", "dfb_snapshot_size", "dfb_snapshot", "dfb_restore",
 ]
 
 _LIB = None
@@ -94,6 +94,9 @@ def lib():
         L.dfb_train_step_raw.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Progress), vp]
         L.dfb_train_step_raw_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
         L.dfb_train_step_raw_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_snapshot_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
+        L.dfb_snapshot.argtypes = [vp, C.c_int, vp, sz]
+        L.dfb_restore.argtypes = [vp, vp, sz, C.POINTER(C.c_int)]
         L.dfb_stream.restype = vp
         L.dfb_stream.argtypes = [vp]
         _LIB = L
@@ -319,6 +322,19 @@ class Engine:
         pr = Progress()
         self._ck(self.L.dfb_read_progress(self.h, C.byref(pr)))
         return pr
+
+    def snapshot(self, save_aux=True):
+        n = C.c_size_t()
+        self._ck(self.L.dfb_snapshot_size(self.h, int(save_aux), C.byref(n)))
+        buf = (C.c_ubyte * max(n.value, 1))()
+        self._ck(self.L.dfb_snapshot(self.h, int(save_aux), buf, n.value))
+        return bytes(buf[:n.value])
+
+    def restore(self, blob):
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        aux = C.c_int()
+        self._ck(self.L.dfb_restore(self.h, buf, len(blob), C.byref(aux)))
+        return bool(aux.value)
 
     def read_entries(self, keys):
         keys = _arr(keys, np.uint64)

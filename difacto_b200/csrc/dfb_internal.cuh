@@ -167,9 +167,10 @@ int launch_lens_scan(const int* lens, size_t n, int* pos, void* cub_tmp, size_t 
                      cudaStream_t s);
 // Loss::Evaluate / BinClassMetric::AUC on device; results added to prog (or written to out)
 int launch_evaluate(const float* label, const float* pred, size_t n, double* out, cudaStream_t s);
-int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp, float* val_tmp,
-               float* key_tmp2, float* val_tmp2, void* cub_tmp, size_t cub_bytes, double* out_add,
-               cudaStream_t s);
+int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp2, float* val_tmp2,
+               void* cub_tmp, size_t cub_bytes, double* out_add, cudaStream_t s);
+int launch_restore(Table& t, const uint64_t* keys, size_t n, const float* scal, const int* vrow,
+                   unsigned long long n_vrows, unsigned seed, cudaStream_t s);
 int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* hasv, float* V,
                         float* cg, int k, cudaStream_t s);
 

@@ -480,6 +480,30 @@ __global__ void k_read_entries(Table t, const int* __restrict__ slot, size_t n, 
   }
 }
 
+// checkpoint restore: insert the saved keys and write their scalar state / row index
+__global__ void k_restore(Table t, const uint64_t* __restrict__ keys, size_t n, const float* __restrict__ scal,
+                          const int* __restrict__ vrow) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  uint64_t h = hash64(key) & t.mask;
+  for (uint64_t probe = 0; probe <= t.mask; ++probe) {
+    const unsigned long long prev = atomicCAS(&t.tab[h].key, kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) {
+      Entry* e = &t.tab[h];
+      e->vrow = vrow[i];
+      e->fea_cnt = scal[i * 4 + 0]; e->w = scal[i * 4 + 1]; e->sqrt_g = scal[i * 4 + 2]; e->z = scal[i * 4 + 3];
+      return;
+    }
+    h = (h + 1) & t.mask;
+  }
+  raise(t.prog, DFB_ERR_CAPACITY);
+}
+
+__global__ void k_set_state(TableState* st, unsigned long long n_keys, unsigned long long n_vrows, unsigned seed) {
+  st->n_keys = n_keys; st->n_vrows = n_vrows; st->seed = seed;
+}
+
 // Loss::Evaluate, loss.h:57-66
 __global__ void k_evaluate(const float* __restrict__ label, const float* __restrict__ pred, size_t n, double* out) {
   __shared__ float red_s[32];
@@ -985,10 +1009,8 @@ int launch_evaluate(const float* label, const float* pred, size_t n, double* out
   return 1;
 }
 
-int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp, float* val_tmp,
-               float* key_tmp2, float* val_tmp2, void* cub_tmp, size_t cub_bytes, double* out_add,
-               cudaStream_t s) {
-  (void)key_tmp; (void)val_tmp;
+int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp2, float* val_tmp2, void* cub_tmp,
+               size_t cub_bytes, double* out_add, cudaStream_t s) {
   if (n == 0) return 0;
   // stable ascending radix sort by pred: ties keep original row order
   cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, pred, key_tmp2, label, val_tmp2, (int)n, 0, 32, s);
@@ -1106,6 +1128,13 @@ int launch_update_pushed(Table& t, const Params& p, const int* slot, const int* 
   }
 #undef DFB_UP
   return -1;
+}
+
+int launch_restore(Table& t, const uint64_t* keys, size_t n, const float* scal, const int* vrow,
+                   unsigned long long n_vrows, unsigned seed, cudaStream_t s) {
+  if (n) k_restore<<<(int)((n + 255) / 256), 256, 0, s>>>(t, keys, n, scal, vrow);
+  k_set_state<<<1, 1, 0, s>>>(t.state, (unsigned long long)n, n_vrows, seed);
+  return 2;
 }
 
 int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* hasv, float* V, float* cg,

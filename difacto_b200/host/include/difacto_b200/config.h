@@ -83,7 +83,8 @@ struct SGDLearnerParam {
   std::string data_in, data_val, data_format = "libsvm", model_out, model_in, loss = "fm";
   int max_num_epochs = 20, num_jobs_per_epoch = 10, batch_size = -1, shuffle = 10;
   float neg_sampling = 1, stop_rel_objv = 1e-5f, stop_val_auc = 1e-5f;
-  int fused = 1;   // engine-only: 1 = one dfb_train_step per batch, 0 = the reference's Pull/Predict/CalcGrad/Push calls
+  int fused = 1;   // engine-only: 1 = raw block -> one device call, 2 = host localizer + one device call,
+                   // 0 = the reference's Pull/Predict/CalcGrad/Push plugin calls
 
   KWArgs InitAllowUnknown(const KWArgs& kwargs) {
     KWArgs remain;

@@ -7,7 +7,10 @@
 // A non-zero C-ABI status becomes a difacto::Error carrying dfb_last_error() (the reference would
 // LOG(FATAL) -> abort()).
 #pragma once
+#include <istream>
+#include <iterator>
 #include <memory>
+#include <ostream>
 #include <string>
 #include <vector>
 
@@ -63,9 +66,21 @@ class GpuSGDUpdater : public Updater {
     }
     return engine_->remain();
   }
-  /** not implemented in the reference either (sgd_updater.h:44-50 are TODO stubs) */
-  void Load(std::istream*, bool*) override {}
-  void Save(bool, std::ostream*) const override {}
+  /** Updater::Load / Save (updater.h:40-47).  TODO stubs in the reference's SGDUpdater
+   * (sgd_updater.h:44-50); here a snapshot of the table in the format of dfb_snapshot. */
+  void Load(std::istream* fi, bool* has_aux) override {
+    std::string blob((std::istreambuf_iterator<char>(*fi)), std::istreambuf_iterator<char>());
+    int aux = 0;
+    engine_->Check(dfb_restore(engine_->handle(), blob.data(), blob.size(), &aux), "dfb_restore");
+    if (has_aux) *has_aux = aux != 0;
+  }
+  void Save(bool save_aux, std::ostream* fo) const override {
+    size_t n = 0;
+    engine_->Check(dfb_snapshot_size(engine_->handle(), save_aux ? 1 : 0, &n), "dfb_snapshot_size");
+    std::string blob(n, '\0');
+    engine_->Check(dfb_snapshot(engine_->handle(), save_aux ? 1 : 0, &blob[0], n), "dfb_snapshot");
+    fo->write(blob.data(), static_cast<std::streamsize>(n));
+  }
 
   /** SGDUpdater::Get, sgd_updater.cc:32-56 */
   void Get(const SArray<feaid_t>& fea_ids, int val_type, SArray<real_t>* weights, SArray<int>* lens) override {

@@ -2,7 +2,9 @@
 // Mirrors src/sgd/sgd_learner.{h,cc} + sgd_utils.h of the reference: epochs -> jobs (file parts) ->
 // minibatches; per-epoch Progress, epoch-end callbacks and the two stop criteria are identical.
 // The minibatch itself (the pull_callback of IterateData, sgd_learner.cc:138-177) is either
-//   fused = 1 (default): one dfb_train_step per batch, the model never leaves HBM, or
+//   fused = 1 (default): one dfb_train_step_raw per batch on the reader's raw block (Localizer::Compact
+//              on the device too), the model never leaves HBM;
+//   fused = 2: host Localizer::Compact, then one dfb_train_step per batch;
 //   fused = 0: the reference's own sequence of plugin calls Store::Pull -> GetPos -> Loss::Predict ->
 //              Evaluate -> penalty -> AUC -> Loss::CalcGrad -> Store::Push through the adapter classes.
 #pragma once
@@ -55,6 +57,7 @@ class SGDLearner : public Learner {
   void RunScheduler() override;
 
  private:
+  void RunEpochs();
   void RunEpoch(int epoch, int job_type, sgd::Progress* prog);
   void IterateData(const sgd::Job& job, sgd::Progress* prog);
   void BatchFused(const RowBlockContainer<unsigned>& data, const std::vector<feaid_t>& keys,

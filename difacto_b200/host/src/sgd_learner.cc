@@ -3,6 +3,7 @@
 #include "difacto_b200/sgd_learner.h"
 
 #include <cstdio>
+#include <fstream>
 
 namespace difacto {
 
@@ -36,8 +37,26 @@ KWArgs SGDLearner::Init(const KWArgs& kwargs) {
   return remain;
 }
 
-// SGDLearner::RunScheduler, sgd_learner.cc:31-68
+// SGDLearner::RunScheduler, sgd_learner.cc:31-68 (+ model_in / model_out, declared in
+// sgd_param.h:53-54 but never acted on by the reference: Job::kLoadModel/kSaveModel are not issued)
 void SGDLearner::RunScheduler() {
+  if (!param_.model_in.empty()) {
+    std::ifstream fi(param_.model_in, std::ios::binary);
+    if (!fi) throw Error("failed to open model_in " + param_.model_in);
+    bool has_aux = false;
+    GetUpdater()->Load(&fi, &has_aux);
+    if (verbose) printf("Loaded model from %s (%s aux data)\n", param_.model_in.c_str(), has_aux ? "with" : "without");
+  }
+  RunEpochs();
+  if (!param_.model_out.empty()) {
+    std::ofstream fo(param_.model_out, std::ios::binary);
+    if (!fo) throw Error("failed to open model_out " + param_.model_out);
+    GetUpdater()->Save(true, &fo);
+    if (verbose) printf("Saved model to %s\n", param_.model_out.c_str());
+  }
+}
+
+void SGDLearner::RunEpochs() {
   real_t pre_loss = 0, pre_val_auc = 0;
   for (int k = 0; k < param_.max_num_epochs; ++k) {
     sgd::Progress train_prog, val_prog;
@@ -172,7 +191,7 @@ void SGDLearner::IterateData(const sgd::Job& job, sgd::Progress* progress) {
                      train ? param_.neg_sampling : 1.0f);
   while (reader.Next()) {
     const bool push_cnt = train && job.epoch == 0;   // :201-202
-    if (param_.fused) {
+    if (param_.fused == 1) {
       // Localizer::Compact + [kFeaCount push] + Pull/Predict/.../Push in one device call on the raw block
       const auto blk = reader.Value();
       const auto& eng = GetUpdater()->engine();
@@ -188,7 +207,8 @@ void SGDLearner::IterateData(const sgd::Job& job, sgd::Progress* progress) {
     std::vector<real_t> feacnt;
     Localizer lc(-1, 2);
     lc.Compact(reader.Value(), &data, &feaids, push_cnt ? &feacnt : nullptr);
-    BatchPluginCalls(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
+    if (param_.fused == 2) BatchFused(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
+    else BatchPluginCalls(data, feaids, push_cnt ? &feacnt : nullptr, train, progress);
   }
 }
 

@@ -169,11 +169,54 @@ static void GpuSGDLearner_Basic() {   // sgd_learner_test.cc:9-49, tolerance 5e-
   for (size_t e = 0; e < losses.size() && e < 20; ++e) EXPECT_LT(std::fabs(losses[e] - kSgdGolden[e]), 2e-4);
 }
 
+static void GpuSGDUpdater_SaveLoad() {
+  // train 5 epochs, save, load into a fresh updater: identical Get() for every key
+  KWArgs args = {{"V_dim", "8"}, {"l1", "0.1"}, {"lr", "0.5"}, {"V_threshold", "1"}, {"table_capacity", "8192"}};
+  GpuSGDUpdater a, b;
+  a.Init(args);
+  b.Init(args);
+  RowBlockContainer<unsigned> data;
+  std::vector<feaid_t> keys;
+  std::vector<real_t> cnt;
+  {
+    BatchReader reader(DataPath(), "libsvm", 0, 1, 100);
+    DFB_CHECK(reader.Next());
+    Localizer lc;
+    lc.Compact(reader.Value(), &data, &keys, &cnt);
+  }
+  for (int ep = 0; ep < 5; ++ep) {
+    dfb_progress pr;
+    a.engine()->Check(dfb_train_step(a.engine()->handle(), data.Size(), reinterpret_cast<const uint64_t*>(data.offset.data()),
+                                     data.index.data(), data.value.data(), data.label.data(), keys.data(), keys.size(),
+                                     ep == 0 ? cnt.data() : nullptr, 1, &pr, nullptr), "step");
+  }
+  std::stringstream ss;
+  a.Save(true, &ss);
+  bool has_aux = false;
+  b.Load(&ss, &has_aux);
+  EXPECT_TRUE(has_aux);
+  SArray<feaid_t> ids(keys.data(), keys.size());
+  SArray<real_t> wa, wb;
+  SArray<int> la, lb;
+  a.Get(ids, Store::kWeight, &wa, &la);
+  b.Get(ids, Store::kWeight, &wb, &lb);
+  EXPECT_EQ(wa.size(), wb.size());
+  EXPECT_TRUE(wa.size() == wb.size() && memcmp(wa.data(), wb.data(), wa.size() * sizeof(real_t)) == 0);
+  EXPECT_TRUE(la.size() == lb.size() && memcmp(la.data(), lb.data(), la.size() * sizeof(int)) == 0);
+  size_t nv = 0;
+  for (int l : la) nv += l > 1;
+  EXPECT_TRUE(nv > 100);
+}
+
 static void GpuSGDLearner_PluginCallsEqualFused() {
   for (const char* vd : {"0", "8"}) {
-    std::vector<double> p1, p0;
+    std::vector<double> p1, p0, p2;
     auto fused = RunBasic("1", vd, &p1);
     auto plugin = RunBasic("0", vd, &p0);
+    auto fused2 = RunBasic("2", vd, &p2);
+    EXPECT_EQ(fused.size(), fused2.size());
+    for (size_t e = 0; e < fused.size() && e < fused2.size(); ++e)
+      EXPECT_LT(std::fabs(fused[e] - fused2[e]), 1e-3 * std::fabs(fused2[e]) + 1e-4);
     EXPECT_EQ(fused.size(), plugin.size());
     for (size_t e = 0; e < fused.size() && e < plugin.size(); ++e) {
       EXPECT_LT(std::fabs(fused[e] - plugin[e]), 1e-3 * std::fabs(plugin[e]) + 1e-4);
@@ -187,7 +230,7 @@ static const Case kCases[] = {
     {"Localizer.Base", Localizer_Base}, {"Localizer.BaseHash", Localizer_BaseHash},
     {"Localizer.ReverseBytes", Localizer_ReverseBytes}, {"ArgParser.LastValueWins", ArgParser_LastValueWins},
     {"GpuFMLoss.NoV", GpuFMLoss_NoV}, {"GpuFMLoss.HasV", GpuFMLoss_HasV},
-    {"GpuSGDLearner.Basic", GpuSGDLearner_Basic},
+    {"GpuSGDLearner.Basic", GpuSGDLearner_Basic}, {"GpuSGDUpdater.SaveLoad", GpuSGDUpdater_SaveLoad},
     {"GpuSGDLearner.PluginCallsEqualFused", GpuSGDLearner_PluginCallsEqualFused}};
 
 int main(int argc, char** argv) {

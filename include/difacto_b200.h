@@ -217,6 +217,15 @@ int dfb_profile_read(dfb_handle h, double* stage_ms, uint64_t* stage_count);
  * ------------------------------------------------------------------------------- */
 int dfb_read_entries(dfb_handle h, const uint64_t* keys, size_t n, float* scal_out,
                      int* has_V_out, float* V_out, float* cg_out);
+/* checkpoint = Updater::Save / Updater::Load (include/difacto/updater.h:40-47; TODO stubs in the
+ * reference's SGDUpdater, sgd_updater.h:44-50, so the byte format is this library's: header +
+ * records in ascending key order {key, fea_cnt, w, [sqrt_g, z], has_V, V[V_dim], [cg[V_dim]]}, the
+ * bracketed fields only with save_aux).  dfb_restore needs an empty table with the same V_dim; a
+ * snapshot without aux data restores a model that can predict but not train ("no aux data",
+ * sgd_updater.cc:75). */
+int dfb_snapshot_size(dfb_handle h, int save_aux, size_t* bytes);
+int dfb_snapshot(dfb_handle h, int save_aux, void* buf, size_t bytes);
+int dfb_restore(dfb_handle h, const void* buf, size_t bytes, int* has_aux_out);
 /* state of the InitV random stream (SGDUpdaterParam::seed after the rand_r calls so far) */
 int dfb_rng_state(dfb_handle h, uint32_t* seed);
 

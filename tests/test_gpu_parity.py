@@ -359,6 +359,47 @@ def test_sorted_scatter_is_bit_reproducible():
         assert np.array_equal(a, b)
 
 
+def test_checkpoint_roundtrip_and_resume():
+    # Updater::Save/Load (updater.h:40-47): restore into a fresh engine, then continue training --
+    # bit-identical to the uninterrupted run (sorted path), incl. the InitV random stream
+    rng = np.random.default_rng(31)
+    kw = dict(V_dim=16, l1=0.05, lr=0.2, V_lr=0.1, V_threshold=1, V_init_scale=0.2, seed=6)
+    batches = [localized(rand_batch(rng, 200, 25, 600, j % 2 == 0)) for j in range(6)]
+
+    def step(E, b, first):
+        return E.train_step(b["offset"], b["lidx"], b["value"], b["label"], b["keys"], b["cnt"] if first else None, True)
+
+    A = engine(**kw)
+    for b in batches[:3]:
+        step(A, b, True)
+    blob = A.snapshot(save_aux=True)
+    B = engine(**kw)
+    assert B.restore(blob) is True
+    assert B.table_stats()["n_keys"] == A.table_stats()["n_keys"] and B.rng_state() == A.rng_state()
+    keys = np.unique(np.concatenate([b["keys"] for b in batches]))
+    for x, y in zip(A.read_entries(keys), B.read_entries(keys)):
+        assert np.array_equal(x, y)
+    for b in batches[3:]:
+        pa, pb = step(A, b, True), step(B, b, True)
+        assert pa.loss == pb.loss
+    for x, y in zip(A.read_entries(keys), B.read_entries(keys)):
+        assert np.array_equal(x, y)
+    assert A.snapshot() == B.snapshot()              # deterministic byte format (ascending keys)
+    # a snapshot without aux data predicts but cannot train (CHECK(has_aux_), sgd_updater.cc:75)
+    C2 = engine(**kw)
+    assert C2.restore(A.snapshot(save_aux=False)) is False
+    b = batches[0]
+    pv = C2.train_step(b["offset"], b["lidx"], b["value"], b["label"], b["keys"], None, False)
+    pa = A.train_step(b["offset"], b["lidx"], b["value"], b["label"], b["keys"], None, False)
+    assert pv.loss == pa.loss
+    with pytest.raises(capi.DfbError):
+        step(C2, b, False)
+    with pytest.raises(capi.DfbError):                # restore needs an empty table / same V_dim
+        A.restore(blob)
+    with pytest.raises(capi.DfbError):
+        engine(**dict(kw, V_dim=8)).restore(blob)
+
+
 def test_async_pipeline_equals_sync():
     rng = np.random.default_rng(12)
     kw = dict(V_dim=32, l1=0.05, lr=0.1, V_threshold=1, seed=4)
