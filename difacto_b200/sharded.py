@@ -402,16 +402,36 @@ def bench_main(args, rank, world, local_rank, benchmod):
         # ---- e2e: per-step H2D of the localized batch from pinned memory + Progress read back ----
         e2e = None
         if not args.no_e2e:
-            for t in range(args.warmup):
-                store.step(to_dev(host[t % nb]), True)
-            E.read_progress()
+            # double-buffered input: the H2D copy of batch t+1 runs on a copy stream while step t computes
+            copy_stream = torch.cuda.Stream(device=dev)
+            main = backend.stream
+
+            def prefetch(h):
+                with torch.cuda.stream(copy_stream):
+                    d = to_dev(h)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                return d, ev
+
+            def run_e2e(nsteps, first):
+                loss = 0.0
+                nxt = prefetch(host[first % nb])
+                for t in range(nsteps):
+                    cur, ev = nxt
+                    if t + 1 < nsteps:
+                        nxt = prefetch(host[(first + t + 1) % nb])
+                    main.wait_event(ev)
+                    store.step(cur, True)
+                    for k2 in ("off", "lab", "lidx", "keys", "cnt"):
+                        cur[k2].record_stream(main)
+                    loss += E.read_progress().loss      # D2H of the step's result
+                return loss
+
+            run_e2e(args.warmup, 0)
             dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            loss_sum = 0.0
-            for t in range(args.steps):
-                store.step(to_dev(host[(args.warmup + t) % nb]), True)
-                loss_sum += E.read_progress().loss
+            loss_sum = run_e2e(args.steps, args.warmup)
             torch.cuda.synchronize()
             dist.barrier()
             dt = torch.tensor([time.perf_counter() - t0], device=dev)
