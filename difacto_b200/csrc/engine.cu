@@ -53,7 +53,16 @@ struct dfb_engine {
   DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
   DevBuf auc_k, auc_v, auc_tmp;
   DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
-  DevBuf l_rkeys, l_skeys, l_pos, l_spos, l_head, l_rank, l_nnzrow, l_keys, l_lidx, l_cnt, l_scal, l_tmp;
+  DevBuf l_rkeys, l_skeys, l_pos, l_spos, l_head, l_rank, l_nnzrow, l_scal, l_tmp;
+  // outputs of the GPU localizer, double-buffered: the localizer of batch t+1 runs on loc_stream
+  // while the step of batch t (which reads set t) runs on the main stream
+  struct LocSet {
+    DevBuf keys, lidx, cnt, occ_sorted, col_start, col_end;
+    cudaEvent_t done = nullptr, consumed = nullptr;
+    bool used = false;
+  } loc[2];
+  uint64_t loc_seq = 0;
+  cudaStream_t loc_stream = nullptr;
   unsigned long long* h_scal = nullptr;   // pinned: {or_all, n_unique}
   DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
   DevBuf scal, hasv, rV, rcg, nvals;
@@ -92,6 +101,7 @@ struct dfb_engine {
     if (b.p) {
       if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sync");
       if ((e = cudaStreamSynchronize(copy_stream)) != cudaSuccess) return cuda_fail(e, "sync");
+      if (loc_stream && (e = cudaStreamSynchronize(loc_stream)) != cudaSuccess) return cuda_fail(e, "sync");
       cudaFree(b.p);
       b.p = nullptr; b.bytes = 0;
     }
@@ -249,10 +259,11 @@ struct StageTimer {
 };
 
 // the fused minibatch on device-resident inputs (everything enqueued on h->stream)
-int ensure_sorted_ws(dfb_engine* h, size_t nrows, size_t nnz, size_t U, bool valued) {
+int ensure_sorted_ws(dfb_engine* h, size_t nrows, size_t nnz, size_t U, bool valued, bool csc_given = false) {
   const int k = h->prm.V_dim;
   DFB_TRY(h->ensure(h->pxv, nrows * (size_t)k * sizeof(float)));
   DFB_TRY(h->ensure(h->p_row, nrows * sizeof(float)));
+  if (csc_given) return 0;
   DFB_TRY(h->ensure(h->occ, nnz * (valued ? 8 : 4)));
   DFB_TRY(h->ensure(h->occ_sorted, nnz * (valued ? 8 : 4)));
   DFB_TRY(h->ensure(h->lidx_sorted, nnz * sizeof(uint32_t)));
@@ -265,7 +276,8 @@ int ensure_sorted_ws(dfb_engine* h, size_t nrows, size_t nnz, size_t U, bool val
 
 int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint32_t* d_idx,
              const float* d_val, const float* d_lab, const uint64_t* d_keys, size_t U, const float* d_cnt,
-             int is_train, bool csc_ready = false) {
+             int is_train, const dfb_engine::LocSet* csc = nullptr) {
+  const bool csc_ready = csc != nullptr;
   if (U > 0x7fffffffULL || nrows > 0x7fffffffULL || nnz > 0x7fffffffULL)
     return h->fail(DFB_ERR_INVALID, "batch too large");
   if (is_train && !h->has_aux) return h->fail(DFB_ERR_INVALID, "no aux data");   // CHECK(has_aux_), sgd_updater.cc:75
@@ -297,7 +309,7 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   v.wv = h->u_wv.as<int2>();
   v.vbase = h->tab.V; v.v_pos = u_vrow; v.vstride = h->tab.rs; v.dense = 0;
   if (sorted) {
-    DFB_TRY(ensure_sorted_ws(h, nrows, nnz, U, d_val != nullptr));
+    DFB_TRY(ensure_sorted_ws(h, nrows, nnz, U, d_val != nullptr, csc_ready));
   } else if (is_train) {
     DFB_TRY(h->ensure(h->gw, U * sizeof(float)));
     DFB_CUDA(h, cudaMemsetAsync(h->gw.p, 0, U * sizeof(float), s));
@@ -361,9 +373,11 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   }
   StageTimer tm_upd(h, 4);
   if (sorted) {
-    int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U, h->col_start.as<int>(), h->col_end.as<int>(),
-                               h->occ_sorted.p, d_val != nullptr, h->p_row.as<float>(), h->pxv.as<float>(), flags,
-                               1, s);
+    int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U,
+                               csc ? csc->col_start.as<int>() : h->col_start.as<int>(),
+                               csc ? csc->col_end.as<int>() : h->col_end.as<int>(),
+                               csc ? csc->occ_sorted.p : h->occ_sorted.p, d_val != nullptr, h->p_row.as<float>(),
+                               h->pxv.as<float>(), flags, 1, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
     h->launches += nl;
     h->launches += launch_initv(h->tab, h->prm, slot, U, flags, pos, h->cub.p, h->cub.bytes, s);
@@ -398,8 +412,7 @@ int collect_one(dfb_engine* h, DevProgress* acc) {
 // view in occ_sorted / col_start / col_end; returns the number of unique keys (two small D2H syncs:
 // the significant key-bit range for the radix sort, then the unique count).
 int localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
-                 const float* d_val, uint64_t max_index, size_t* U_out) {
-  cudaStream_t s = h->stream;
+                 const float* d_val, uint64_t max_index, dfb_engine::LocSet& L, cudaStream_t s, size_t* U_out) {
   *U_out = 0;
   if (nnz > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "batch too large");   // localizer.cc:19-20
   if (max_index == 0) return h->fail(DFB_ERR_INVALID, "max_index must be > 0");
@@ -411,14 +424,14 @@ int localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off,
   DFB_TRY(h->ensure(h->l_head, n1 * 4));
   DFB_TRY(h->ensure(h->l_rank, n1 * 4));
   DFB_TRY(h->ensure(h->l_nnzrow, n1 * 4));
-  DFB_TRY(h->ensure(h->l_keys, n1 * 8));
-  DFB_TRY(h->ensure(h->l_lidx, n1 * 4));
-  DFB_TRY(h->ensure(h->l_cnt, n1 * 4));
   DFB_TRY(h->ensure(h->l_scal, 16));
   DFB_TRY(h->ensure(h->l_tmp, localize_sort_tmp_bytes(nnz)));
-  DFB_TRY(h->ensure(h->occ_sorted, n1 * (d_val ? 8 : 4)));
-  DFB_TRY(h->ensure(h->col_start, n1 * 4));
-  DFB_TRY(h->ensure(h->col_end, n1 * 4));
+  DFB_TRY(h->ensure(L.keys, n1 * 8));
+  DFB_TRY(h->ensure(L.lidx, n1 * 4));
+  DFB_TRY(h->ensure(L.cnt, n1 * 4));
+  DFB_TRY(h->ensure(L.occ_sorted, n1 * (d_val ? 8 : 4)));
+  DFB_TRY(h->ensure(L.col_start, n1 * 4));
+  DFB_TRY(h->ensure(L.col_end, n1 * 4));
   if (nnz == 0) return 0;
   unsigned long long* scal = h->l_scal.as<unsigned long long>();
   h->launches += launch_localize_keys(d_ids, nnz, max_index, h->l_rkeys.as<unsigned long long>(),
@@ -432,27 +445,39 @@ int localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off,
   h->launches += launch_localize_sort(h->l_rkeys.as<unsigned long long>(), h->l_pos.as<uint32_t>(), nnz, begin_bit,
                                       h->l_skeys.as<unsigned long long>(), h->l_spos.as<uint32_t>(),
                                       h->l_head.as<int>(), h->l_rank.as<int>(), h->l_tmp.p, h->l_tmp.bytes,
-                                      h->l_nnzrow.as<uint32_t>(), d_val, h->l_keys.as<uint64_t>(),
-                                      h->col_start.as<int>(), h->col_end.as<int>(), h->l_lidx.as<uint32_t>(),
-                                      h->occ_sorted.p, scal + 1, s);
+                                      h->l_nnzrow.as<uint32_t>(), d_val, L.keys.as<uint64_t>(),
+                                      L.col_start.as<int>(), L.col_end.as<int>(), L.lidx.as<uint32_t>(),
+                                      L.occ_sorted.p, scal + 1, s);
   DFB_CUDA(h, cudaMemcpyAsync(h->h_scal + 1, scal + 1, 8, cudaMemcpyDeviceToHost, s));
   DFB_CUDA(h, cudaStreamSynchronize(s));
   *U_out = (size_t)h->h_scal[1];
   return 0;
 }
 
-// raw (un-localized) CSR<u64> minibatch: Localizer::Compact + the fused step, all on the device
+// raw (un-localized) CSR<u64> minibatch: Localizer::Compact + the fused step, all on the device.
+// The localizer runs on its own stream into one of two output sets, so while the host waits for
+// the two 8-byte results of batch t+1 the main stream is still busy with the step of batch t.
 int step_raw_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
-                 const float* d_val, const float* d_lab, int push_cnt, int is_train) {
+                 const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready) {
+  dfb_engine::LocSet& L = h->loc[h->loc_seq & 1];
+  cudaStream_t ls = h->loc_stream;
+  if (inputs_ready) DFB_CUDA(h, cudaStreamWaitEvent(ls, inputs_ready, 0));
+  if (L.used) DFB_CUDA(h, cudaStreamWaitEvent(ls, L.consumed, 0));
   size_t U = 0;
-  DFB_TRY(localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, &U));   // Localizer(-1, ...), sgd_learner.cc:203
+  DFB_TRY(localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, L, ls, &U));   // Localizer(-1, ...), sgd_learner.cc:203
   const float* d_cnt = nullptr;
   if (push_cnt && U) {
-    h->launches += launch_cnt_from_cols(h->col_start.as<int>(), h->col_end.as<int>(), U, h->l_cnt.as<float>(), h->stream);
-    d_cnt = h->l_cnt.as<float>();
+    h->launches += launch_cnt_from_cols(L.col_start.as<int>(), L.col_end.as<int>(), U, L.cnt.as<float>(), ls);
+    d_cnt = L.cnt.as<float>();
   }
-  return step_dev(h, nrows, nnz, d_off, h->l_lidx.as<uint32_t>(), d_val, d_lab, h->l_keys.as<uint64_t>(), U, d_cnt,
-                  is_train, /*csc_ready=*/true);
+  DFB_CUDA(h, cudaEventRecord(L.done, ls));
+  DFB_CUDA(h, cudaStreamWaitEvent(h->stream, L.done, 0));
+  int rc = step_dev(h, nrows, nnz, d_off, L.lidx.as<uint32_t>(), d_val, d_lab, L.keys.as<uint64_t>(), U, d_cnt,
+                    is_train, &L);
+  DFB_CUDA(h, cudaEventRecord(L.consumed, h->stream));
+  L.used = true;
+  h->loc_seq++;
+  return rc;
 }
 
 int check_csr(dfb_engine* h, size_t nrows, const uint64_t* offset) {
@@ -540,6 +565,11 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
+  if ((e = cudaStreamCreateWithFlags(&h->loc_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
+  for (auto& L : h->loc) {
+    if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&L.consumed, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
+  }
   if ((e = cudaEventCreateWithFlags(&h->ev_fm_done, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
   if ((e = cudaEventCreateWithFlags(&h->ev_auc_done, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
   for (auto& s : h->in) {
@@ -583,8 +613,15 @@ int dfb_destroy(dfb_handle h) {
   if (!h) return DFB_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&h->u_wv, &h->l_rkeys, &h->l_skeys, &h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow, &h->l_keys,
-                    &h->l_lidx, &h->l_cnt, &h->l_scal, &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
+  for (auto& L : h->loc) {
+    DevBuf* lb[] = {&L.keys, &L.lidx, &L.cnt, &L.occ_sorted, &L.col_start, &L.col_end};
+    for (auto* b : lb) if (b->p) cudaFree(b->p);
+    if (L.done) cudaEventDestroy(L.done);
+    if (L.consumed) cudaEventDestroy(L.consumed);
+  }
+  if (h->loc_stream) cudaStreamDestroy(h->loc_stream);
+  DevBuf* bufs[] = {&h->u_wv, &h->l_rkeys, &h->l_skeys, &h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow,
+                    &h->l_scal, &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
                     &h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
                     &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
                     &h->a_val, &h->a_lab, &h->a_w, &h->a_wpos, &h->a_vpos, &h->a_pred, &h->a_grad, &h->scal,
@@ -898,6 +935,7 @@ int dfb_sync(dfb_handle h) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
   DFB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->loc_stream));
   DFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return DFB_OK;
 }
@@ -1011,12 +1049,14 @@ int dfb_localize(dfb_handle h, size_t nrows, const uint64_t* offset, const uint6
   DFB_TRY(h2d(h, h->a_off, offset, (nrows + 1) * sizeof(uint64_t), s));
   DFB_TRY(h2d(h, h->keys, index, nnz * sizeof(uint64_t), s));
   size_t U = 0;
-  DFB_TRY(localize_dev(h, nrows, nnz, h->a_off.as<uint64_t>(), h->keys.as<uint64_t>(), nullptr, max_index, &U));
-  DFB_CUDA(h, cudaMemcpyAsync(index_out, h->l_lidx.p, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  DFB_CUDA(h, cudaMemcpyAsync(keys_out, h->l_keys.p, U * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaStreamSynchronize(h->loc_stream));
+  dfb_engine::LocSet& L = h->loc[0];
+  DFB_TRY(localize_dev(h, nrows, nnz, h->a_off.as<uint64_t>(), h->keys.as<uint64_t>(), nullptr, max_index, L, s, &U));
+  DFB_CUDA(h, cudaMemcpyAsync(index_out, L.lidx.p, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  DFB_CUDA(h, cudaMemcpyAsync(keys_out, L.keys.p, U * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   if (cnt_out) {
-    h->launches += launch_cnt_from_cols(h->col_start.as<int>(), h->col_end.as<int>(), U, h->l_cnt.as<float>(), s);
-    DFB_CUDA(h, cudaMemcpyAsync(cnt_out, h->l_cnt.p, U * sizeof(float), cudaMemcpyDeviceToHost, s));
+    h->launches += launch_cnt_from_cols(L.col_start.as<int>(), L.col_end.as<int>(), U, L.cnt.as<float>(), s);
+    DFB_CUDA(h, cudaMemcpyAsync(cnt_out, L.cnt.p, U * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   DFB_CUDA(h, cudaStreamSynchronize(s));
   *nkeys = U;
@@ -1027,7 +1067,7 @@ int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_
                            const float* d_value_or_null, const float* d_label, int push_cnt, int is_train) {
   if (!h) return DFB_ERR_INVALID;
   DFB_CUDA(h, cudaSetDevice(h->device));
-  return step_raw_dev(h, nrows, nnz, d_offset, d_ids, d_value_or_null, d_label, push_cnt, is_train);
+  return step_raw_dev(h, nrows, nnz, d_offset, d_ids, d_value_or_null, d_label, push_cnt, is_train, nullptr);
 }
 
 int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
@@ -1048,7 +1088,7 @@ int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset,
   DFB_CUDA(h, cudaEventRecord(in.copied, cs));
   DFB_CUDA(h, cudaStreamWaitEvent(h->stream, in.copied, 0));
   int rc = step_raw_dev(h, nrows, nnz, in.off.as<uint64_t>(), in.ids.as<uint64_t>(),
-                        value ? in.val.as<float>() : nullptr, in.lab.as<float>(), push_cnt, is_train);
+                        value ? in.val.as<float>() : nullptr, in.lab.as<float>(), push_cnt, is_train, in.copied);
   DFB_CUDA(h, cudaEventRecord(in.consumed, h->stream));
   h->seq++;
   if (rc != 0) return rc;

@@ -38,8 +38,16 @@ __global__ void k_rev_keys(const uint64_t* __restrict__ ids, size_t n, unsigned 
     pos[j] = (uint32_t)j;
   }
   // OR of all keys: the radix sort only needs the bit range that is not constant zero
+  // (warp shuffle -> shared memory -> one atomic per block)
+  __shared__ unsigned long long s_or[8];
   for (int o = 16; o > 0; o >>= 1) k |= __shfl_xor_sync(0xffffffffu, k, o);
-  if ((threadIdx.x & 31) == 0 && k) atomicOr(or_all, k);
+  if ((threadIdx.x & 31) == 0) s_or[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a |= s_or[w];
+    if (a) atomicOr(or_all, a);
+  }
 }
 
 // row id of every nnz position (one warp per row, coalesced)
