@@ -79,6 +79,64 @@ static void Localizer_ReverseBytes() {
   }
 }
 
+// tests/cpp/batch_reader_test.cc:9-57 (same goldens)
+static const int kBatch = 37;
+static const int kLabelSum[] = {11, 15, 10};
+static const int kLen[] = {37, 37, 26};
+static const size_t kOffSum[] = {85035, 63968, 31323};
+static const uint64_t kIdxSum[] = {95285478, 70504854, 62972349};
+static const float kValNorm[] = {37.0f, 37.0f, 26.0f};
+
+static void BatchReader_Read() {
+  BatchReader reader(DataPath(), "libsvm", 0, 1, kBatch);
+  int i = 0;
+  while (reader.Next() && i < 3) {
+    auto b = reader.Value();
+    double ls = 0;
+    for (size_t r = 0; r < b.size; ++r) ls += b.label[r];
+    EXPECT_EQ(static_cast<int>(ls), kLabelSum[i]);
+    EXPECT_EQ(static_cast<int>(b.size), kLen[i]);
+    EXPECT_EQ(static_cast<size_t>(norm1(b.offset, b.size + 1)), kOffSum[i]);
+    EXPECT_EQ(static_cast<uint64_t>(norm1(b.index, b.offset[b.size])), kIdxSum[i]);
+    EXPECT_LT(std::fabs(kValNorm[i] - norm2(b.value, b.offset[b.size])), 1e-4);
+    ++i;
+  }
+  EXPECT_EQ(i, 3);
+}
+
+static void BatchReader_RandRead() {
+  BatchReader reader(DataPath(), "libsvm", 0, 1, kBatch, kBatch);
+  int i = 0;
+  while (reader.Next() && i < 3) {
+    auto b = reader.Value();
+    double ls = 0;
+    for (size_t r = 0; r < b.size; ++r) ls += b.label[r];
+    EXPECT_EQ(static_cast<int>(ls), kLabelSum[i]);
+    EXPECT_EQ(static_cast<int>(b.size), kLen[i]);
+    EXPECT_TRUE(static_cast<size_t>(norm1(b.offset, b.size + 1)) != kOffSum[i]);   // shuffled rows
+    EXPECT_EQ(static_cast<uint64_t>(norm1(b.index, b.offset[b.size])), kIdxSum[i]);
+    EXPECT_LT(std::fabs(kValNorm[i] - norm2(b.value, b.offset[b.size])), 1e-4);
+    ++i;
+  }
+  EXPECT_EQ(i, 3);
+}
+
+static void BatchReader_PartRead() {
+  BatchReader reader(DataPath(), "libsvm", 1, 2, kBatch);
+  int ttl = 0;
+  while (reader.Next()) {
+    auto b = reader.Value();
+    EXPECT_LT(std::fabs(static_cast<double>(b.size) - norm2(b.value, b.offset[b.size])), 1e-4);
+    ttl += static_cast<int>(b.size);
+  }
+  EXPECT_TRUE(ttl <= 60 && ttl >= 40);
+  // the two halves partition the file: no row lost or duplicated
+  BatchReader other(DataPath(), "libsvm", 0, 2, kBatch);
+  int ttl0 = 0;
+  while (other.Next()) ttl0 += static_cast<int>(other.Value().size);
+  EXPECT_EQ(ttl + ttl0, 100);
+}
+
 static void ArgParser_LastValueWins() {
   ArgParser p;
   p.AddArg("V_dim=64");
@@ -229,6 +287,8 @@ struct Case { const char* name; void (*fn)(); };
 static const Case kCases[] = {
     {"Localizer.Base", Localizer_Base}, {"Localizer.BaseHash", Localizer_BaseHash},
     {"Localizer.ReverseBytes", Localizer_ReverseBytes}, {"ArgParser.LastValueWins", ArgParser_LastValueWins},
+    {"BatchReader.Read", BatchReader_Read}, {"BatchReader.RandRead", BatchReader_RandRead},
+    {"BatchReader.PartRead", BatchReader_PartRead},
     {"GpuFMLoss.NoV", GpuFMLoss_NoV}, {"GpuFMLoss.HasV", GpuFMLoss_HasV},
     {"GpuSGDLearner.Basic", GpuSGDLearner_Basic}, {"GpuSGDUpdater.SaveLoad", GpuSGDUpdater_SaveLoad},
     {"GpuSGDLearner.PluginCallsEqualFused", GpuSGDLearner_PluginCallsEqualFused}};
