@@ -103,3 +103,69 @@ def test_cli_model_out_then_model_in(host_bin, libsvm_fixture, tmp_path):
     second, so2 = losses(["max_num_epochs=10", f"model_in={model}"])
     assert "Loaded model" in so2
     assert second[0] < first[0] and abs(second[0] - full[10]) < 0.05 * full[10]
+
+
+def _write_synthetic_libsvm(path, rows, nnz, id_space, seed, binary):
+    rng = np.random.default_rng(seed)
+    batches = []
+    with open(path, "w") as f:
+        for r in range(rows):
+            n = int(rng.integers(1, nnz + 1))
+            ids = np.unique(rng.zipf(1.3, n) % id_space)
+            lab = 1 if rng.random() < 0.3 else -1
+            if binary:
+                f.write(f"{lab} " + " ".join(f"{int(i)}:1" for i in ids) + "\n")
+            else:
+                vals = (rng.random(len(ids)).astype(np.float32) + 0.1)
+                f.write(f"{lab} " + " ".join(f"{int(i)}:{v:.9g}" for i, v in zip(ids, vals)) + "\n")
+
+
+def _oracle_epoch_losses(path, conf, batch_size, epochs):
+    """replay of SGDLearner::IterateData with the oracle: file order batches (shuffle=0), 1 job per epoch"""
+    from oracle import oracle as O
+    rows = [l.split() for l in open(path).read().strip().split("\n")]
+    M = O.Oracle(**conf)
+    losses = []
+    for ep in range(epochs):
+        prog = np.zeros(5, np.float32)
+        for b0 in range(0, len(rows), batch_size):
+            chunk = rows[b0:b0 + batch_size]
+            lab = np.array([float(r[0]) for r in chunk], np.float32)
+            idx, val, off = [], [], [0]
+            for r in chunk:
+                for t in r[1:]:
+                    i, v = t.split(":")
+                    idx.append(int(i))
+                    val.append(np.float32(v))
+                off.append(len(idx))
+            val = np.array(val, np.float32)
+            if np.all(val == 1):
+                val = None          # BatchReader drops all-ones values (batch_reader.cc:71-73)
+            M.sgd_step(np.array(off, np.uint64), np.array(idx, np.uint64), val, lab, True, ep == 0, progress=prog)
+        losses.append(float(prog[0]))
+    return losses
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,conf,binary", [
+    # BASELINE.json configs: rcv1_sgd.conf + V_dim=16; criteo_sgd.conf as shipped (V_dim=10: generic kernels);
+    # criteo l1-regularised FTRL with V_dim=32
+    ("rcv1_v16", dict(l1=1, lr=.1, V_dim=16, V_threshold=2), False),
+    ("criteo_v10", dict(l1=10, l2=10, V_dim=10, V_threshold=10, V_l2=10), True),
+    ("criteo_ftrl_v32", dict(l1=2, l2=1, lr=.5, V_dim=32, V_threshold=5, V_l2=1), True),
+])
+def test_cli_conf_runs_match_oracle(host_bin, tmp_path, name, conf, binary):
+    data = str(tmp_path / f"{name}.libsvm")
+    _write_synthetic_libsvm(data, rows=1500, nnz=30, id_space=3000, seed=11, binary=binary)
+    conffile = tmp_path / f"{name}.conf"
+    conffile.write_text("# generated\n" + f"data_in = {data}\nlearner = sgd\ntask = train\nmax_num_epochs = 4\n"
+                        "batch_size = 500\nnum_jobs_per_epoch = 1\nshuffle = 0\nstop_rel_objv = 0\ntable_capacity = 16384\n"
+                        + "".join(f"{k} = {v}\n" for k, v in conf.items()))
+    exe = os.path.join(host_bin, "difacto_b200")
+    ref = _oracle_epoch_losses(data, conf, 500, 4)
+    for fused in ("1", "0"):
+        out = subprocess.run([exe, f"argfile={conffile}", f"fused={fused}"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = [float(l.split("loss = ")[1].split(",")[0]) for l in out.stdout.split("\n") if "Training: loss" in l]
+        assert len(got) == 4
+        assert np.allclose(got, ref, rtol=2e-4, atol=1e-3), (name, fused, got, ref)
