@@ -362,9 +362,12 @@ def main_b200(args, rank, world, local_rank):
             raw.append(dict(off=torch.from_numpy(off).pin_memory(), lab=torch.from_numpy(lab).pin_memory(),
                             ids=torch.from_numpy(ids.view(np.int64)).pin_memory()))
 
-        def submit_raw(b):
+        def submit_raw(b, nxt=None):
             r = raw[b]
             E.train_step_raw_async(B, r["off"], r["ids"], None, r["lab"], False, True)
+            if nxt is not None:       # start the H2D of the next batch while this step runs
+                n_ = raw[nxt]
+                E.prefetch_raw(B, n_["off"], n_["ids"], None, n_["lab"])
         for t in range(args.warmup):
             submit_raw(t % nb)
         E.read_progress()
@@ -372,7 +375,7 @@ def main_b200(args, rank, world, local_rank):
         t0 = time.perf_counter()
         loss_sum = 0.0
         for t in range(args.steps):
-            submit_raw((args.warmup + t) % nb)
+            submit_raw((args.warmup + t) % nb, (args.warmup + t + 1) % nb if t + 1 < args.steps else None)
             if t >= 1:
                 loss_sum += E.wait_step().loss
         loss_sum += E.wait_step().loss
@@ -382,7 +385,7 @@ def main_b200(args, rank, world, local_rank):
         e2e_raw = {"value": args.steps * B / dt, "unit": "examples/s",
                    "h2d_bytes_per_step": int((B + 1) * 8 + N * 8 + B * 4), "d2h_bytes_per_step": 64 + 16,
                    "ms_per_step": dt / args.steps * 1e3,
-                   "api": "dfb_train_step_raw_async + dfb_wait_step: raw uint64 CSR from pinned host memory, "
+                   "api": "dfb_train_step_raw_async (+ dfb_prefetch_raw) + dfb_wait_step: raw uint64 CSR from pinned host memory, "
                           "Localizer::Compact on the GPU, then the fused step"}
     sampler.stop()
     clocks = sampler.summary(wall0, time.time())   # value + stage + forward-only + e2e regions: all under load

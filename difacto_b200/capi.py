@@ -34,7 +34,7 @@ EXPORTS = [
     "dfb_wait_step", "dfb_profile", "dfb_profile_read",
     "dfb_peer_alloc", "dfb_peer_open", "dfb_peer_close", "dfb_peer_free", "dfb_dev_pull_rows_peer",
     "dfb_dev_fm_step_peer", "dfb_localize", "dfb_train_step_raw", "dfb_train_step_raw_async",
-    "dfb_train_step_raw_dev", "dfb_snapshot_size", "dfb_snapshot", "dfb_restore",
+    "dfb_train_step_raw_dev", "dfb_prefetch_raw", "dfb_snapshot_size", "dfb_snapshot", "dfb_restore",
 ]
 
 _LIB = None
@@ -93,6 +93,7 @@ def lib():
         L.dfb_localize.argtypes = [vp, sz, vp, vp, u64, vp, vp, vp, C.POINTER(sz)]
         L.dfb_train_step_raw.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Progress), vp]
         L.dfb_train_step_raw_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_prefetch_raw.argtypes = [vp, sz, vp, vp, vp, vp]
         L.dfb_train_step_raw_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, C.c_int, C.c_int]
         L.dfb_snapshot_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
         L.dfb_snapshot.argtypes = [vp, C.c_int, vp, sz]
@@ -285,6 +286,9 @@ class Engine:
     def train_step_raw_async(self, nrows, offset, ids, value, label, push_cnt=False, is_train=True):
         self._ck(self.L.dfb_train_step_raw_async(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label),
                                                  int(push_cnt), int(is_train)))
+
+    def prefetch_raw(self, nrows, offset, ids, value, label):
+        self._ck(self.L.dfb_prefetch_raw(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label)))
 
     def train_step_raw_dev(self, nrows, nnz, d_offset, d_ids, d_value, d_label, push_cnt=False, is_train=True):
         self._ck(self.L.dfb_train_step_raw_dev(self.h, nrows, nnz, _p(d_offset), _p(d_ids), _p(d_value), _p(d_label),

@@ -67,7 +67,12 @@ struct dfb_engine {
   DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
   DevBuf scal, hasv, rV, rcg, nvals;
   // double-buffered inputs of the pipelined step
-  struct InSet { DevBuf off, idx, val, lab, keys, cnt, ids; cudaEvent_t copied = nullptr, consumed = nullptr; } in[2];
+  struct InSet {
+    DevBuf off, idx, val, lab, keys, cnt, ids;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+    const void* pre_ids = nullptr;     // host batch already staged by dfb_prefetch_raw (identity check)
+    size_t pre_nrows = 0, pre_nnz = 0;
+  } in[2];
   uint64_t seq = 0;
   // per-step Progress snapshots of the pipelined path (pinned ring + completion events)
   static constexpr int kRing = 8;
@@ -968,6 +973,7 @@ int dfb_train_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, con
   const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
   if (nnz && !index) return h->fail(DFB_ERR_INVALID, "index is NULL");
   auto& in = h->in[h->seq & 1];
+  in.pre_ids = nullptr;
   cudaStream_t cs = h->copy_stream;
   // the copy of batch t+1 may overwrite set b only after batch t-1 (same set) was consumed
   if (h->seq >= 2) DFB_CUDA(h, cudaStreamWaitEvent(cs, in.consumed, 0));
@@ -1070,6 +1076,33 @@ int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_
   return step_raw_dev(h, nrows, nnz, d_offset, d_ids, d_value_or_null, d_label, push_cnt, is_train, nullptr);
 }
 
+// H2D of one raw batch into the input set the next submission will use (copy stream)
+static int stage_raw(dfb_handle h, dfb_engine::InSet& in, size_t nrows, size_t nnz, const uint64_t* offset,
+                     const uint64_t* ids, const float* value, const float* label) {
+  cudaStream_t cs = h->copy_stream;
+  if (h->seq >= 2) DFB_CUDA(h, cudaStreamWaitEvent(cs, in.consumed, 0));
+  DFB_TRY(h2d(h, in.off, offset, (nrows + 1) * sizeof(uint64_t), cs));
+  DFB_TRY(h2d(h, in.ids, ids, nnz * sizeof(uint64_t), cs));
+  if (value) DFB_TRY(h2d(h, in.val, value, nnz * sizeof(float), cs));
+  DFB_TRY(h2d(h, in.lab, label, nrows * sizeof(float), cs));
+  DFB_CUDA(h, cudaEventRecord(in.copied, cs));
+  return 0;
+}
+
+int dfb_prefetch_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids, const float* value,
+                     const float* label) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_TRY(check_csr(h, nrows, offset));
+  if (nrows && !label) return h->fail(DFB_ERR_INVALID, "label is NULL");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
+  if (nnz && !ids) return h->fail(DFB_ERR_INVALID, "ids is NULL");
+  auto& in = h->in[h->seq & 1];
+  DFB_TRY(stage_raw(h, in, nrows, nnz, offset, ids, value, label));
+  in.pre_ids = ids; in.pre_nrows = nrows; in.pre_nnz = nnz;
+  return DFB_OK;
+}
+
 int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
                              const float* value, const float* label, int push_cnt, int is_train) {
   if (!h) return DFB_ERR_INVALID;
@@ -1079,13 +1112,9 @@ int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset,
   const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
   if (nnz && !ids) return h->fail(DFB_ERR_INVALID, "ids is NULL");
   auto& in = h->in[h->seq & 1];
-  cudaStream_t cs = h->copy_stream;
-  if (h->seq >= 2) DFB_CUDA(h, cudaStreamWaitEvent(cs, in.consumed, 0));
-  DFB_TRY(h2d(h, in.off, offset, (nrows + 1) * sizeof(uint64_t), cs));
-  DFB_TRY(h2d(h, in.ids, ids, nnz * sizeof(uint64_t), cs));
-  if (value) DFB_TRY(h2d(h, in.val, value, nnz * sizeof(float), cs));
-  DFB_TRY(h2d(h, in.lab, label, nrows * sizeof(float), cs));
-  DFB_CUDA(h, cudaEventRecord(in.copied, cs));
+  if (!(in.pre_ids == ids && ids && in.pre_nrows == nrows && in.pre_nnz == nnz))
+    DFB_TRY(stage_raw(h, in, nrows, nnz, offset, ids, value, label));
+  in.pre_ids = nullptr;
   DFB_CUDA(h, cudaStreamWaitEvent(h->stream, in.copied, 0));
   int rc = step_raw_dev(h, nrows, nnz, in.off.as<uint64_t>(), in.ids.as<uint64_t>(),
                         value ? in.val.as<float>() : nullptr, in.lab.as<float>(), push_cnt, is_train, in.copied);

@@ -190,6 +190,10 @@ int dfb_train_step_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const
 int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
                              const float* value_or_null, const float* label, int push_cnt,
                              int is_train);
+/* optional double-buffering hint: start the H2D copy of the batch the NEXT dfb_train_step_raw_async call
+ * will be given (same pointers), so that the copy overlaps the step submitted before it */
+int dfb_prefetch_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                     const float* value_or_null, const float* label);
 int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset,
                            const uint64_t* d_ids, const float* d_value_or_null, const float* d_label,
                            int push_cnt, int is_train);

@@ -100,8 +100,11 @@ def test_raw_async_pipeline():
     tot = 0.0
     for (o, l, i, v) in batches:
         tot += S.train_step_raw(o, i, v, l, push_cnt=True).loss
-    for (o, l, i, v) in batches:
+    for j, (o, l, i, v) in enumerate(batches):
         A.train_step_raw_async(len(l), o, i, None, l, push_cnt=True)
+        if j + 1 < len(batches) and j % 2 == 0:      # prefetch every other batch: both paths interleave
+            o2, l2, i2, _ = batches[j + 1]
+            A.prefetch_raw(len(l2), o2, i2, None, l2)
     got = sum(A.wait_step().loss for _ in batches)
     assert abs(got - tot) <= 1e-5 * abs(tot)
     keys = np.unique(np.concatenate([O.reverse_bytes_np(b[2]) for b in batches]))
