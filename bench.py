@@ -474,6 +474,7 @@ def main_b200(args, rank, world, local_rank):
 
 def main():
     args = parse_args()
+    args.warmup = max(args.warmup, 3)      # timing hygiene: never fewer than 3 untimed warm-up steps
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -497,6 +497,8 @@ extern "C" {
 
 const char* dfb_last_error(dfb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+int dfb_destroy(dfb_handle h);
+
 int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_handle* out) {
   if (!out) { g_create_error = "out is NULL"; return DFB_ERR_INVALID; }
   *out = nullptr;
@@ -562,7 +564,8 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   cudaError_t e;
   auto cfail = [&](const char* what) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
-    delete h;
+    cudaGetLastError();   // clear the sticky error before releasing what was created so far
+    dfb_destroy(h);
     return (int)DFB_ERR_CUDA;
   };
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) return cfail("cudaSetDevice");
@@ -585,7 +588,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   t.max_keys = (uint64_t)table_capacity;
   t.cap = next_pow2(2 * t.max_keys);
   if (t.cap < 1024) t.cap = 1024;
-  if (t.cap > (1ULL << 31)) { g_create_error = "table_capacity too large (slots are 31-bit)"; delete h; return DFB_ERR_PARAM; }
+  if (t.cap > (1ULL << 31)) { g_create_error = "table_capacity too large (slots are 31-bit)"; dfb_destroy(h); return DFB_ERR_PARAM; }
   t.mask = t.cap - 1;
   t.ks = (p.V_dim + 3) / 4 * 4;
   t.vcap = (uint64_t)v_capacity;
