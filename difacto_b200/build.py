@@ -18,6 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr", "-Xptxas", "-v",
          "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+FLAGS += os.environ.get("DFB_EXTRA_NVCC_FLAGS", "").split()      # tuning experiments (e.g. -DDFB_FM_MINBLOCKS=4)
 
 
 def _digest():

@@ -80,8 +80,11 @@ __device__ __forceinline__ void block_add_loss(float loss_acc, size_t nrows, Dev
 // MODE 0: predict only.  MODE 1: training with fp32 red.global scatter into dense gradient rows.
 // MODE 2: training, "emit": writes p_i, p_i*XV_i and the (row[,x]) payload of every nnz so that
 //         the gradient can be reduced per key without atomics (kernels_table.cu: k_bwd_update).
+#ifndef DFB_FM_MINBLOCKS
+#define DFB_FM_MINBLOCKS 4
+#endif
 template <int K, int MODE, bool HAS_VAL>
-__global__ void __launch_bounds__(256) k_fm_fast(FmBatch b, FmView v) {
+__global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, FmView v) {
   constexpr bool TRAIN = MODE == 1;
   constexpr int LPR = K / 4;                 // lanes per V row, one float4 each
   constexpr int G = 32 / LPR;                // V rows fetched by one warp-wide load

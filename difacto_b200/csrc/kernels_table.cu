@@ -604,8 +604,14 @@ __device__ __forceinline__ void load_occ(const void* occ, int o, uint32_t& row, 
 // UNRB row-groups in flight; the first occurrence's p*XV row is fetched together with V|cg.
 // SRC 0: gradient reduced from the occurrence lists (fused step / worker).  SRC 1: gradient read
 // from dense rows gw_in[n], gV_in[n][K] that a worker pushed (owner side of the sharded store).
+#ifndef DFB_BU_MINBLOCKS
+#define DFB_BU_MINBLOCKS 1
+#endif
+#ifndef DFB_BU_UNRB
+#define DFB_BU_UNRB 2
+#endif
 template <int K, bool HAS_VAL, bool APPLY, int SRC = 0>
-__global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int* __restrict__ slot,
+__global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, Params p, const int* __restrict__ slot,
                                                     const int* __restrict__ pull_vrow, size_t n,
                                                     const int* __restrict__ col_start,
                                                     const int* __restrict__ col_end,
@@ -618,7 +624,7 @@ __global__ void __launch_bounds__(256) k_bwd_update(Table t, Params p, const int
   constexpr int LPR = K / 4;
   constexpr int G = 32 / LPR;
   constexpr int NPASS = 32 / G;
-  constexpr int UNRB = NPASS >= 2 ? 2 : 1;
+  constexpr int UNRB = NPASS >= DFB_BU_UNRB ? DFB_BU_UNRB : 1;
   constexpr int kHeavy = 64;     // occurrence-list length above which a key is reduced cooperatively
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
