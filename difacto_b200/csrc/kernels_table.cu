@@ -605,7 +605,7 @@ __device__ __forceinline__ void load_occ(const void* occ, int o, uint32_t& row, 
 // SRC 0: gradient reduced from the occurrence lists (fused step / worker).  SRC 1: gradient read
 // from dense rows gw_in[n], gV_in[n][K] that a worker pushed (owner side of the sharded store).
 #ifndef DFB_BU_MINBLOCKS
-#define DFB_BU_MINBLOCKS 1
+#define DFB_BU_MINBLOCKS 4
 #endif
 #ifndef DFB_BU_UNRB
 #define DFB_BU_UNRB 2
