@@ -169,3 +169,29 @@ def test_cli_conf_runs_match_oracle(host_bin, tmp_path, name, conf, binary):
         got = [float(l.split("loss = ")[1].split(",")[0]) for l in out.stdout.split("\n") if "Training: loss" in l]
         assert len(got) == 4
         assert np.allclose(got, ref, rtol=2e-4, atol=1e-3), (name, fused, got, ref)
+
+
+@pytest.mark.gpu
+def test_cli_validation_epochs(host_bin, libsvm_fixture, tmp_path):
+    """data_val: every epoch runs a validation pass (Pull + Predict only, sgd_learner.cc:41-44,158-171);
+    with data_val == data_in the validation loss of epoch k equals the training loss of epoch k+1's forward
+    only if the model did not change -- so compare against the oracle's predict-only replay instead"""
+    from oracle import oracle as O
+    exe = os.path.join(host_bin, "difacto_b200")
+    conf = dict(V_dim=8, l1=0.1, lr=0.5, V_threshold=1)
+    out = subprocess.run([exe, f"data_in={libsvm_fixture}", f"data_val={libsvm_fixture}", "batch_size=100", "shuffle=0",
+                          "num_jobs_per_epoch=1", "max_num_epochs=5", "stop_rel_objv=0", "stop_val_auc=-1",
+                          "table_capacity=8192"] + [f"{k}={v}" for k, v in conf.items()], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    tr = [float(l.split("loss = ")[1].split(",")[0]) for l in out.stdout.split("\n") if "Training: loss" in l]
+    va = [float(l.split("loss = ")[1].split(",")[0]) for l in out.stdout.split("\n") if "Validation: loss" in l]
+    auc = [float(l.split("AUC = ")[1]) for l in out.stdout.split("\n") if "Validation: loss" in l]
+    assert len(tr) == 5 and len(va) == 5
+    d = np.load(os.path.join(ROOT, "tests", "golden", "rcv1_100.npz"))
+    M = O.Oracle(**conf)
+    for ep in range(5):
+        pt = M.sgd_step(d["offset"], d["index"], d["value"], d["label"], True, ep == 0)
+        pv = M.sgd_step(d["offset"], d["index"], d["value"], d["label"], False, False)
+        assert abs(tr[ep] - float(pt[0])) <= 2e-4 * abs(float(pt[0])) + 1e-3
+        assert abs(va[ep] - float(pv[0])) <= 2e-4 * abs(float(pv[0])) + 1e-3
+        assert abs(auc[ep] - float(pv[2]) / 100.0) < 5e-3
