@@ -269,6 +269,12 @@ def main_b200(args, rank, world, local_rank):
     E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap,
                     overlap_auc=0 if args.no_overlap_auc else 1, **extra, **kw)
     ks = E.row_stride()
+    # the product's own localizer (Localizer::Compact on the GPU) must agree bit for bit with the harness's numpy one
+    _, _, ids0 = gen_raw_batch(args, 1)
+    gl, gk, gc = E.localize(host[0]["off"].numpy(), ids0)
+    localizer_check = bool(np.array_equal(gl.view(np.int32), host[0]["lidx"].numpy())
+                           and np.array_equal(gk.view(np.int64), host[0]["keys"].numpy())
+                           and np.array_equal(gc, host[0]["cnt"].numpy()))
     devb = [dict(off=h["off"].to(dev), lab=h["lab"].to(dev), lidx=h["lidx"].to(dev), keys=h["keys"].to(dev),
                  cnt=h["cnt"].to(dev), U=h["U"]) for h in host]
     torch.cuda.synchronize()
@@ -467,6 +473,7 @@ def main_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches), "clocks": clocks,
         "stages_ms_per_step": {n: s["ms"] / max(s["count"], 1) for n, s in stages.items()},
         "loss_per_example": prog.loss / max(prog.nrows, 1), "datagen_s": t_gen,
+        "gpu_localizer_equals_numpy_localizer": localizer_check,
     }
     print(json.dumps(line))
     E.close()
