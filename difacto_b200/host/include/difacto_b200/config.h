@@ -81,6 +81,7 @@ class ArgParser {
 /** SGDLearnerParam, src/sgd/sgd_param.h:12-64: same keys, defaults and required fields */
 struct SGDLearnerParam {
   std::string data_in, data_val, data_format = "libsvm", model_out, model_in, loss = "fm";
+  std::string pred_out;   // engine-only: where task=predict writes one prediction per input row
   int max_num_epochs = 20, num_jobs_per_epoch = 10, batch_size = -1, shuffle = 10;
   float neg_sampling = 1, stop_rel_objv = 1e-5f, stop_val_auc = 1e-5f;
   int fused = 1;   // engine-only: 1 = raw block -> one device call, 2 = host localizer + one device call,
@@ -97,6 +98,7 @@ struct SGDLearnerParam {
         else if (k == "data_format") data_format = v;
         else if (k == "model_out") model_out = v;
         else if (k == "model_in") model_in = v;
+        else if (k == "pred_out") pred_out = v;
         else if (k == "loss") loss = v;
         else if (k == "max_num_epochs") max_num_epochs = std::stoi(v);
         else if (k == "num_jobs_per_epoch") num_jobs_per_epoch = std::stoi(v);

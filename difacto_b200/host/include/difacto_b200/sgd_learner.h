@@ -50,6 +50,10 @@ class SGDLearner : public Learner {
   KWArgs Init(const KWArgs& kwargs) override;
   void AddEpochEndCallback(const EpochCallback& cb) { epoch_end_callback_.push_back(cb); }
   GpuSGDUpdater* GetUpdater() { return static_cast<GpuSGDUpdater*>(store_->updater().get()); }
+  /** task=predict (a `LOG(FATAL) << "TODO"` in the reference, main.cc:61-62): load model_in, run the forward pass
+   * over data_in in file order and write one prediction (the clamped FM score, fm_loss.h:118) per row to pred_out;
+   * returns the Progress (loss, AUC*n, nrows) of the pass */
+  sgd::Progress Predict();
   /** set false to silence the per-epoch log lines */
   bool verbose = true;
 

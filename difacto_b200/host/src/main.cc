@@ -44,7 +44,12 @@ int main(int argc, char* argv[]) {
       learner->Run();
       delete learner;
     } else if (task == "predict") {
-      throw Error("TODO");   // main.cc:61-62 of the reference: LOG(FATAL) << "TODO"
+      // a TODO in the reference (main.cc:61-62): forward pass of a saved model over data_in
+      if (learner_type != "sgd") throw Error("task=predict is implemented for learner=sgd");
+      SGDLearner learner;
+      KWArgs unknown = learner.Init(remain);
+      for (const auto& kv : unknown) fprintf(stderr, " - unrecognized %s = %s\n", kv.first.c_str(), kv.second.c_str());
+      learner.Predict();
     } else if (task == "convert") {
       throw Error("task=convert (data format conversion) is host I/O outside the accelerated path");
     } else {

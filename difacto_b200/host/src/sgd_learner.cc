@@ -56,6 +56,32 @@ void SGDLearner::RunScheduler() {
   }
 }
 
+sgd::Progress SGDLearner::Predict() {
+  if (param_.model_in.empty()) throw Error("task=predict needs model_in");
+  std::ifstream fi(param_.model_in, std::ios::binary);
+  if (!fi) throw Error("failed to open model_in " + param_.model_in);
+  bool has_aux = false;
+  GetUpdater()->Load(&fi, &has_aux);
+  FILE* fo = param_.pred_out.empty() ? nullptr : fopen(param_.pred_out.c_str(), "w");
+  if (!param_.pred_out.empty() && !fo) throw Error("failed to open pred_out " + param_.pred_out);
+  sgd::Progress prog;
+  const auto& eng = GetUpdater()->engine();
+  BatchReader reader(param_.data_in, param_.data_format, 0, 1, 65536u);
+  std::vector<real_t> pred;
+  while (reader.Next()) {
+    const auto blk = reader.Value();
+    pred.assign(blk.size, 0.f);
+    dfb_progress pr;
+    eng->Check(dfb_train_step_raw(eng->handle(), blk.size, reinterpret_cast<const uint64_t*>(blk.offset), blk.index,
+                                  blk.value, blk.label, 0, 0, &pr, pred.data()), "dfb_train_step_raw");
+    prog.loss += pr.loss; prog.penalty += pr.penalty; prog.auc += pr.auc; prog.nrows += pr.nrows;
+    if (fo) for (real_t p : pred) fprintf(fo, "%.9g\n", p);
+  }
+  if (fo) fclose(fo);
+  if (verbose) printf(" - Prediction: %s, rows = %g\n", prog.TextString().c_str(), prog.nrows);
+  return prog;
+}
+
 void SGDLearner::RunEpochs() {
   real_t pre_loss = 0, pre_val_auc = 0;
   for (int k = 0; k < param_.max_num_epochs; ++k) {

@@ -53,8 +53,11 @@ def test_cli_conf_surface(host_bin, tmp_path, libsvm_fixture):
     # batch_size is a required field (src/sgd/sgd_param.h:58): the README quick-start line fails the same way
     out = subprocess.run([exe, f"data_in={libsvm_fixture}", "V_dim=2", "dry_run=1"], capture_output=True, text=True)
     assert out.returncode != 0 and "batch_size" in out.stderr
-    out = subprocess.run([exe, "task=predict", f"data_in={libsvm_fixture}", "batch_size=1"], capture_output=True, text=True)
-    assert out.returncode != 0 and "TODO" in out.stderr
+    out = subprocess.run([exe, "task=predict", f"data_in={libsvm_fixture}", "batch_size=1", "dry_run=1"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and "task = predict" in out.stdout
+    out = subprocess.run([exe, "task=convert", f"data_in={libsvm_fixture}", "batch_size=1"], capture_output=True, text=True)
+    assert out.returncode != 0 and "convert" in out.stderr
 
 
 @pytest.mark.gpu
@@ -195,3 +198,31 @@ def test_cli_validation_epochs(host_bin, libsvm_fixture, tmp_path):
         assert abs(tr[ep] - float(pt[0])) <= 2e-4 * abs(float(pt[0])) + 1e-3
         assert abs(va[ep] - float(pv[0])) <= 2e-4 * abs(float(pv[0])) + 1e-3
         assert abs(auc[ep] - float(pv[2]) / 100.0) < 5e-3
+
+
+@pytest.mark.gpu
+def test_cli_task_predict(host_bin, libsvm_fixture, tmp_path, rcv1):
+    """task=predict (TODO in the reference, main.cc:61-62): forward pass of a saved model"""
+    from oracle import oracle as O
+    exe = os.path.join(host_bin, "difacto_b200")
+    conf = ["V_dim=8", "l1=0.1", "lr=0.5", "V_threshold=1", "batch_size=100", "num_jobs_per_epoch=1", "shuffle=0",
+            "stop_rel_objv=0", "table_capacity=8192"]
+    model, preds = str(tmp_path / "m.dfb"), str(tmp_path / "pred.txt")
+    out = subprocess.run([exe, f"data_in={libsvm_fixture}", "max_num_epochs=6", f"model_out={model}"] + conf,
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    out = subprocess.run([exe, "task=predict", f"data_in={libsvm_fixture}", f"model_in={model}", f"pred_out={preds}"] + conf,
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = np.loadtxt(preds, dtype=np.float32)
+    assert got.shape == (100,)
+    M = O.Oracle(V_dim=8, l1=0.1, lr=0.5, V_threshold=1)
+    for ep in range(6):
+        M.sgd_step(rcv1["offset"], rcv1["index"], rcv1["value"], rcv1["label"], True, ep == 0)
+    lidx, keys, _ = O.localize(rcv1["offset"], rcv1["index"])
+    vals, lens = M.get(keys)
+    w_pos, V_pos = O.get_pos(lens)
+    ref = O.fm_predict(8, rcv1["offset"], lidx, rcv1["value"], vals, w_pos, V_pos)
+    assert np.allclose(got, ref, rtol=2e-3, atol=2e-3)
+    loss = float(out.stdout.split("loss = ")[1].split(",")[0])
+    assert abs(loss - O.evaluate(rcv1["label"], ref)) <= 2e-3 * abs(loss) + 1e-2
