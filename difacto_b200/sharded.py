@@ -235,7 +235,6 @@ class PeerShardedStore(ShardedStore):
 
     def step(self, batch, is_train=True, push_cnt=False):
         S, U, ks, me, E = self.S, batch["U"], self.ks, self.rank, self.b.E
-        assert U <= self.Umax, "batch has more keys than the pull buffer (max_keys)"
         self._mark("begin")
         bounds = [int(x) for x in batch["bounds"]]
         send = [bounds[i + 1] - bounds[i] for i in range(S)]
@@ -249,7 +248,13 @@ class PeerShardedStore(ShardedStore):
             M = t_all.view(S, S).tolist()          # M[r][s] = keys rank r sends to owner s
         recv = [int(M[r][me]) for r in range(S)]
         R = sum(recv)
-        assert R <= self.Rmax, "more keys received than the push buffer holds (max_recv_keys)"
+        # every rank sees the whole count matrix, so a buffer overflow anywhere is detected by all ranks
+        # in the same step (a local assert on one rank would leave the others waiting in a collective)
+        worst_R = max(sum(int(M[r][s]) for r in range(S)) for s in range(S))
+        worst_U = max(sum(int(x) for x in M[r]) for r in range(S))
+        if worst_R > self.Rmax or worst_U > self.Umax:
+            raise RuntimeError(f"peer buffers too small: a rank receives {worst_R} keys (max_recv_keys={self.Rmax}) "
+                               f"or sends {worst_U} keys (max_keys={self.Umax}); recreate PeerShardedStore with larger sizes")
         seg = [0]
         for r in range(S):
             seg.append(seg[-1] + recv[r])
