@@ -12,8 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdifacto_b200.so")
-SOURCES = ["kernels_fm.cu", "kernels_table.cu", "kernels_localize.cu", "engine.cu"]
-HEADERS = ["dfb_internal.cuh", os.path.join("..", "..", "include", "difacto_b200.h")]
+SOURCES = ["kernels_fm.cu", "kernels_table.cu", "kernels_localize.cu", "kernels_shard.cu", "engine.cu", "shard.cu"]
+HEADERS = ["dfb_internal.cuh", "dfb_device.cuh", "engine_internal.cuh", "shard_layout.cuh",
+           os.path.join("..", "..", "include", "difacto_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -35,6 +35,8 @@ EXPORTS = [
     "dfb_peer_alloc", "dfb_peer_open", "dfb_peer_close", "dfb_peer_free", "dfb_dev_pull_rows_peer",
     "dfb_dev_fm_step_peer", "dfb_localize", "dfb_train_step_raw", "dfb_train_step_raw_async",
     "dfb_train_step_raw_dev", "dfb_prefetch_raw", "dfb_snapshot_size", "dfb_snapshot", "dfb_restore",
+    "dfb_shard_init", "dfb_shard_export", "dfb_shard_connect", "dfb_shard_step_dev", "dfb_shard_step_async",
+    "dfb_shard_info",
 ]
 
 _LIB = None
@@ -98,6 +100,13 @@ def lib():
         L.dfb_snapshot_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
         L.dfb_snapshot.argtypes = [vp, C.c_int, vp, sz]
         L.dfb_restore.argtypes = [vp, vp, sz, C.POINTER(C.c_int)]
+        L.dfb_shard_init.argtypes = [vp, C.c_int, C.c_int, sz, sz, sz, sz, C.POINTER(sz)]
+        L.dfb_shard_export.argtypes = [vp, C.POINTER(vp), vp]
+        L.dfb_shard_connect.argtypes = [vp, vp]
+        L.dfb_shard_step_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_shard_step_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_shard_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz), C.POINTER(sz),
+                                     C.POINTER(u64)]
         L.dfb_stream.restype = vp
         L.dfb_stream.argtypes = [vp]
         _LIB = L
@@ -386,6 +395,37 @@ class Engine:
         gV = (C.c_void_p * nseg)(*[int(x) for x in peer_gV])
         self._ck(self.L.dfb_dev_fm_step_peer(self.h, nrows, nnz, _p(d_off), _p(d_idx), _p(d_val), _p(d_lab), nkeys,
                                              _p(d_w), _p(d_hasv), _p(d_V), nseg, sb, gw, gV, int(first_seg)))
+
+    # ---- the NVLink-sharded store behind the C-ABI (dfb_shard_*) ----
+    def shard_init(self, rank, nranks, max_rows, max_nnz, seg_keys=0, seg_nnz=0):
+        n = C.c_size_t()
+        self._ck(self.L.dfb_shard_init(self.h, rank, nranks, max_rows, max_nnz, seg_keys, seg_nnz, C.byref(n)))
+        return n.value
+
+    def shard_export(self):
+        """(mailbox device pointer, 64-byte CUDA IPC handle)"""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._ck(self.L.dfb_shard_export(self.h, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def shard_connect(self, peer_ptrs):
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p) if p else 0) for p in peer_ptrs])
+        self._ck(self.L.dfb_shard_connect(self.h, arr))
+
+    def shard_step_dev(self, nrows, nnz, d_offset, d_ids, d_value, d_label, push_cnt=False, is_train=True):
+        self._ck(self.L.dfb_shard_step_dev(self.h, nrows, nnz, _p(d_offset), _p(d_ids), _p(d_value), _p(d_label),
+                                           int(push_cnt), int(is_train)))
+
+    def shard_step_async(self, nrows, offset, ids, value, label, push_cnt=False, is_train=True):
+        self._ck(self.L.dfb_shard_step_async(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label),
+                                             int(push_cnt), int(is_train)))
+
+    def shard_info(self):
+        r, n = C.c_int(), C.c_int()
+        sk, sn, st = C.c_size_t(), C.c_size_t(), C.c_uint64()
+        self._ck(self.L.dfb_shard_info(self.h, C.byref(r), C.byref(n), C.byref(sk), C.byref(sn), C.byref(st)))
+        return dict(rank=r.value, nranks=n.value, seg_keys=sk.value, seg_nnz=sn.value, steps=st.value)
 
     def dev_push_rows(self, d_keys, n, d_gw, d_hasv, d_gV):
         self._ck(self.L.dfb_dev_push_rows(self.h, _p(d_keys), n, _p(d_gw), _p(d_hasv), _p(d_gV)))

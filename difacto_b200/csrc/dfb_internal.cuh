@@ -81,6 +81,9 @@ struct FmView {
   const int* gv_pos;
   long long gvstride;
   float* gxxp;
+  // 1: per-load L2 policies -- the per-nnz {w,vrow} view and the p*XV rows are re-read (evict_last), the
+  // V rows are touched once (evict_first)
+  int l2hint;
 };
 
 // where the worker's gradient rows go: locally contiguous (nseg == 0) or, per owner segment of the
@@ -91,6 +94,44 @@ struct SegDst {
   int bounds[9];      // key index boundaries of the segments (nseg + 1 used)
   float* gw[8];       // per segment: destination of gw for the segment's first key
   float* gV[8];       // per segment: destination row of gV for the segment's first key
+};
+
+// owner side of the fused sharded store (SRC 2 of k_bwd_update): what differs from the single-GPU update
+struct ShardApply {
+  const float* w_pulled;        // w of every key as pulled at step start (penalty of the pulled weights)
+  const unsigned char* conf;    // != 0: a lower-rank worker's push already updated this key in this step ...
+  const float* vsave;           // ... and this is its V row as pulled at step start ([n][K])
+};
+
+// forward "partials" of the fused sharded store (MODE 3 of k_fm_fast): the owner of a key segment computes,
+// for every row of every worker's minibatch, the part of the FM interaction that is linear in ITS rows
+//   XV_i^(s) = sum_{j in segment s} x_ij V_j,  sum_j (x_ij V_j)^2,  sum_j x_ij w_j
+// and stores it straight into that worker's mailbox (peer memory over NVLink).
+// what a worker tells the owner of a key segment about its minibatch (written into the owner's mailbox)
+struct ShardHdr {
+  unsigned long long nkeys;   // keys of the worker's batch that fall into this owner's range
+  unsigned long long nnz;     // non-zeros over those keys
+  unsigned long long nrows;   // rows of the worker's batch
+  unsigned long long flags;   // bit 0: is_train, bit 1: push_cnt, bit 2: valued
+  unsigned long long step;
+  unsigned long long pad[3];
+};
+static_assert(sizeof(ShardHdr) == 64, "ShardHdr is one 64-byte record");
+__host__ __device__ inline unsigned long long shard_hdr_nrows(const ShardHdr* h) { return h->nrows; }
+
+struct PartSrc {
+  const uint64_t* rowptr;   // [nrows+1] offsets into ridx (this worker's rows restricted to my key segment)
+  const uint32_t* ridx;     // key index relative to the segment
+  const float* rval;        // values (nullptr: binary)
+  const int2* wv;           // pulled view {bits(w), vrow} of the segment's keys
+  const ShardHdr* hdr;      // nrows of the worker's batch
+  float* out_xv;            // [nrows][K]   (peer memory)
+  float2* out_sc;           // [nrows] {sum (xV)^2, sum x w}
+};
+struct PartArgs {
+  int nsrc, rot;            // rot: first source this owner starts with (staggers the peers' inbound traffic)
+  unsigned long long bcap;  // rows are enumerated as src * bcap + row
+  PartSrc s[8];
 };
 
 struct FmBatch {
@@ -119,6 +160,8 @@ bool fm_fast_supported(int V_dim);
 // ---- launchers (kernels_fm.cu) ----
 // returns number of kernel launches performed, or <0 on invalid configuration
 int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t s);
+// MODE 3: partial interaction sums of every source's rows (see PartArgs); v.vbase/vstride = the table rows
+int launch_fm_partial(int V_dim, bool valued, const FmView& v, const PartArgs& pa, cudaStream_t s);
 int launch_grad_finalize(int V_dim, size_t nkeys, const float* weights, const int* V_pos,
                          const float* xxp, float* grad, cudaStream_t s);
 
@@ -129,16 +172,18 @@ int launch_grad_finalize_dense(int V_dim, int ks, size_t nkeys, const int* hasv,
 int launch_table_init(Table& t, unsigned seed, cudaStream_t s);
 // find (or insert) keys; slot_out[i] = hash position or -1.  When pull outputs are non-null also
 // emits w and vrow of each entry.
-int launch_lookup(Table& t, const uint64_t* keys, size_t n, bool insert, int* slot_out,
-                  float* w_out, int* vrow_out, int2* wv_out, cudaStream_t s);
+// n is a host count, or (dn != nullptr) the capacity with the actual count read from the device
+int launch_lookup(Table& t, const uint64_t* keys, size_t n, const unsigned long long* dn, bool insert,
+                  int* slot_out, float* w_out, int* vrow_out, int2* wv_out, cudaStream_t s);
 // SGDUpdater::Update(kFeaCount) incl. the InitV pass.  flags/pos/cub_tmp are workspaces of n ints.
-int launch_feacnt(Table& t, const Params& p, const int* slot, size_t n, const float* cnt,
-                  int* flags, int* pos, void* cub_tmp, size_t cub_bytes, cudaStream_t s);
+// counts: cnt[n], or (cnt == nullptr) the differences of cnt_cols[n+1].  ws: (n+31)/32 + 2 ints.
+int launch_feacnt(Table& t, const Params& p, const int* slot, size_t n, const unsigned long long* dn,
+                  const float* cnt, const int* cnt_cols, int* flags, int* ws, cudaStream_t s);
 size_t scan_tmp_bytes(size_t n);
 size_t sort_tmp_bytes(size_t n);
 // InitV for flagged keys, consuming the rand_r stream in key order (sgd_updater.cc:140-147)
-int launch_initv(Table& t, const Params& p, const int* slot, size_t n, int* flags, int* pos,
-                 void* cub_tmp, size_t cub_bytes, cudaStream_t s);
+int launch_initv(Table& t, const Params& p, const int* slot, size_t n, const unsigned long long* dn,
+                 int* flags, int* ws, cudaStream_t s);
 // SGDUpdater::Get packing: lens -> scan -> ragged [w, V...] (sgd_updater.cc:32-56)
 int launch_pack_ragged(Table& t, const Params& p, const int* slot, size_t n, int* lens, int* pos,
                        float* vals, unsigned long long* nvals_out, void* cub_tmp, size_t cub_bytes,
@@ -160,9 +205,9 @@ int launch_update_ragged(Table& t, const Params& p, const int* slot, size_t n, c
                          const int* lens_or_null, const int* pos, int* flags, cudaStream_t s);
 // penalty over a pulled view without updating (validation batches, sharded worker)
 int launch_penalty(const Params& p, DevProgress* prog, const float* w_arr, const int* vrow,
-                   const float* V, int ks, int dense, size_t n, cudaStream_t s);
-int launch_pull_view(Table& t, const int* slot, size_t n, float* w_out, int* vrow_out,
-                     int2* wv_out, cudaStream_t s);
+                   const float* V, int ks, int dense, size_t n, const unsigned long long* dn, cudaStream_t s);
+int launch_pull_view(Table& t, const int* slot, size_t n, const unsigned long long* dn, float* w_out,
+                     int* vrow_out, int2* wv_out, cudaStream_t s);
 int launch_lens_scan(const int* lens, size_t n, int* pos, void* cub_tmp, size_t cub_bytes,
                      cudaStream_t s);
 // Loss::Evaluate / BinClassMetric::AUC on device; results added to prog (or written to out)
@@ -183,7 +228,7 @@ int launch_localize_sort(const unsigned long long* rkeys, const uint32_t* pos, s
                          unsigned long long* skeys, uint32_t* spos, int* head, int* rank1, void* tmp,
                          size_t tmp_bytes, const uint32_t* nnz_row, const float* value, uint64_t* keys_out,
                          int* col_start, int* col_end, uint32_t* lidx_out, void* occ_sorted,
-                         unsigned long long* n_unique, cudaStream_t s);
+                         unsigned long long* scal /* {or_all, n_unique} */, DevProgress* prog, cudaStream_t s);
 int launch_cnt_from_cols(const int* col_start, const int* col_end, size_t n, float* cnt, cudaStream_t s);
 
 // ---- sorted (atomic-free, deterministic) gradient reduction ----
@@ -197,9 +242,9 @@ int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t 
 // per key: grad = sum_occ x * pXV[row] - V * XXp, then either FTRL/AdaGrad in place (apply) or
 // complete dense gradient rows out (gw_out, gV_out = sum - V_pulled*XXp; the sharded worker).
 int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,
-                      const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
-                      const float* p_row, const float* pxv, int* flags, int accumulate_penalty,
-                      cudaStream_t s);
+                      const unsigned long long* dn, const int* col_start, const int* col_end,
+                      const void* occ_sorted, bool valued, const float* p_row, const float* pxv, int* flags,
+                      int accumulate_penalty, const ShardApply* shard, cudaStream_t s);
 int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_pulled,
                      const int* hasv, size_t n, const int* col_start, const int* col_end,
                      const void* occ_sorted, bool valued, const float* p_row, const float* pxv,

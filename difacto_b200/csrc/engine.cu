@@ -16,118 +16,31 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/difacto_b200.h"
-#include "dfb_internal.cuh"
+#include "engine_internal.cuh"
 
 using namespace dfb;  // NOLINT
+
+int dfb_engine::ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes && b.p) return 0;
+  if (bytes == 0) bytes = 16;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e;
+  if (b.p) {
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sync");
+    if ((e = cudaStreamSynchronize(copy_stream)) != cudaSuccess) return cuda_fail(e, "sync");
+    if (loc_stream && (e = cudaStreamSynchronize(loc_stream)) != cudaSuccess) return cuda_fail(e, "sync");
+    if (shard) dfbh::shard_sync(this);
+    cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+  }
+  if ((e = cudaMalloc(&b.p, want)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+  b.bytes = want;
+  return 0;
+}
 
 namespace {
 
 thread_local std::string g_create_error;
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  template <typename T> T* as() const { return static_cast<T*>(p); }
-};
-
-}  // namespace
-
-struct dfb_engine {
-  Params prm;
-  int device = 0;
-  int compute_auc = 1;
-  int force_generic = 0;
-  int scatter_sorted = 1;   // 1: atomic-free sorted reduction (deterministic); 0: red.global atomics
-  int overlap_auc = 1;
-  int has_aux = 1;          // false after restoring a snapshot saved without aux data (sgd_updater.h:88)      // run the AUC kernels on the auxiliary stream, concurrently with the update
-  cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
-  cudaEvent_t ev_fm_done = nullptr, ev_auc_done = nullptr;
-  Table tab;
-  std::string err;
-  std::vector<std::pair<std::string, std::string>> unknown;
-  uint64_t launches = 0;
-
-  // workspaces (grown on demand)
-  DevBuf u_wv;
-  DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
-  DevBuf auc_k, auc_v, auc_tmp;
-  DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
-  DevBuf l_rkeys, l_skeys, l_pos, l_spos, l_head, l_rank, l_nnzrow, l_scal, l_tmp;
-  // outputs of the GPU localizer, double-buffered: the localizer of batch t+1 runs on loc_stream
-  // while the step of batch t (which reads set t) runs on the main stream
-  struct LocSet {
-    DevBuf keys, lidx, cnt, occ_sorted, col_start, col_end;
-    cudaEvent_t done = nullptr, consumed = nullptr;
-    bool used = false;
-  } loc[2];
-  uint64_t loc_seq = 0;
-  cudaStream_t loc_stream = nullptr;
-  unsigned long long* h_scal = nullptr;   // pinned: {or_all, n_unique}
-  DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
-  DevBuf scal, hasv, rV, rcg, nvals;
-  // double-buffered inputs of the pipelined step
-  struct InSet {
-    DevBuf off, idx, val, lab, keys, cnt, ids;
-    cudaEvent_t copied = nullptr, consumed = nullptr;
-    const void* pre_ids = nullptr;     // host batch already staged by dfb_prefetch_raw (identity check)
-    size_t pre_nrows = 0, pre_nnz = 0;
-  } in[2];
-  uint64_t seq = 0;
-  // per-step Progress snapshots of the pipelined path (pinned ring + completion events)
-  static constexpr int kRing = 8;
-  DevProgress* h_ring = nullptr;
-  cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  uint64_t submitted = 0, collected = 0;
-  DevProgress backlog;             // snapshots folded in when the ring was full
-  // optional per-stage CUDA-event timing (bench.py's roofline numbers)
-  static constexpr int kStages = 5;      // lookup+pull, fm, auc, csc sort, update(+initv)
-  static constexpr int kProfRing = 32;
-  int profile = 0;
-  std::vector<cudaEvent_t> pev;          // [kProfRing][kStages][2]
-  std::vector<char> pev_used;            // [kProfRing][kStages]
-  uint64_t prof_steps = 0;
-  double stage_ms[kStages] = {0, 0, 0, 0, 0};
-  uint64_t stage_n[kStages] = {0, 0, 0, 0, 0};
-  DevProgress* h_prog = nullptr;   // pinned
-  unsigned long long* h_nvals = nullptr;  // pinned
-
-  int fail(int code, const std::string& msg) { err = msg; return code; }
-  int cuda_fail(cudaError_t e, const char* what) {
-    err = std::string(what) + ": " + cudaGetErrorString(e);
-    return DFB_ERR_CUDA;
-  }
-  // grow a workspace; frees/reallocs only after the compute stream has drained
-  int ensure(DevBuf& b, size_t bytes) {
-    if (bytes <= b.bytes && b.p) return 0;
-    if (bytes == 0) bytes = 16;
-    size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e;
-    if (b.p) {
-      if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sync");
-      if ((e = cudaStreamSynchronize(copy_stream)) != cudaSuccess) return cuda_fail(e, "sync");
-      if (loc_stream && (e = cudaStreamSynchronize(loc_stream)) != cudaSuccess) return cuda_fail(e, "sync");
-      cudaFree(b.p);
-      b.p = nullptr; b.bytes = 0;
-    }
-    if ((e = cudaMalloc(&b.p, want)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
-    b.bytes = want;
-    return 0;
-  }
-};
-
-namespace {
-
-#define DFB_CUDA(h, call)                                                  \
-  do {                                                                     \
-    cudaError_t _e = (call);                                               \
-    if (_e != cudaSuccess) return (h)->cuda_fail(_e, #call);               \
-  } while (0)
-#define DFB_TRY(expr)              \
-  do {                             \
-    int _rc = (expr);              \
-    if (_rc != 0) return _rc;      \
-  } while (0)
 
 uint64_t next_pow2(uint64_t x) {
   uint64_t p = 1;
@@ -205,16 +118,19 @@ int fetch_scratch(dfb_engine* h, DevProgress* out) {
   return 0;
 }
 
-int ensure_key_ws(dfb_engine* h, size_t n) {
+}  // namespace
+int dfbh::ensure_key_ws(dfb_engine* h, size_t n) {
   DFB_TRY(h->ensure(h->slot, n * sizeof(int)));
   DFB_TRY(h->ensure(h->u_w, n * sizeof(float)));
   DFB_TRY(h->ensure(h->u_vrow, n * sizeof(int)));
   DFB_TRY(h->ensure(h->u_wv, n * sizeof(int2)));
   DFB_TRY(h->ensure(h->flags, n * sizeof(int)));
-  DFB_TRY(h->ensure(h->pos, n * sizeof(int)));
+  DFB_TRY(h->ensure(h->pos, (n + 64) * sizeof(int)));     // also the tile workspace of the InitV pass
   DFB_TRY(h->ensure(h->cub, scan_tmp_bytes(n)));
   return 0;
 }
+using dfbh::ensure_key_ws;
+namespace {
 
 int h2d(dfb_engine* h, DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
   DFB_TRY(h->ensure(b, bytes));
@@ -279,10 +195,14 @@ int ensure_sorted_ws(dfb_engine* h, size_t nrows, size_t nnz, size_t U, bool val
   return 0;
 }
 
+// U is the number of keys, or (dU != nullptr) the capacity of the key arrays with the actual count on the device
+// (a batch localized on the GPU never reports its size to the host); d_cnt / cnt_cols: see launch_feacnt.
 int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint32_t* d_idx,
              const float* d_val, const float* d_lab, const uint64_t* d_keys, size_t U, const float* d_cnt,
-             int is_train, const dfb_engine::LocSet* csc = nullptr) {
+             int is_train, const dfb_engine::LocSet* csc = nullptr, const unsigned long long* dU = nullptr,
+             const int* cnt_cols = nullptr) {
   const bool csc_ready = csc != nullptr;
+  const bool push_cnt = d_cnt != nullptr || cnt_cols != nullptr;
   if (U > 0x7fffffffULL || nrows > 0x7fffffffULL || nnz > 0x7fffffffULL)
     return h->fail(DFB_ERR_INVALID, "batch too large");
   if (is_train && !h->has_aux) return h->fail(DFB_ERR_INVALID, "no aux data");   // CHECK(has_aux_), sgd_updater.cc:75
@@ -300,12 +220,15 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   // Push(kFeaCount) then Pull (sgd_learner.cc:214-217, :177)
   {
   StageTimer tm(h, 0);
-  if (d_cnt) {
-    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, nullptr, nullptr, nullptr, s);
-    h->launches += launch_feacnt(h->tab, h->prm, slot, U, d_cnt, flags, pos, h->cub.p, h->cub.bytes, s);
-    h->launches += launch_pull_view(h->tab, slot, U, u_w, u_vrow, h->u_wv.as<int2>(), s);
+  // a validation / prediction batch must not grow the table: a missing entry reads as w = 0, no V
+  // (what a default-constructed SGDEntry would give), so nothing needs to be inserted
+  const bool insert = is_train || push_cnt;
+  if (push_cnt) {
+    h->launches += launch_lookup(h->tab, d_keys, U, dU, true, slot, nullptr, nullptr, nullptr, s);
+    h->launches += launch_feacnt(h->tab, h->prm, slot, U, dU, d_cnt, cnt_cols, flags, pos, s);
+    h->launches += launch_pull_view(h->tab, slot, U, dU, u_w, u_vrow, h->u_wv.as<int2>(), s);
   } else {
-    h->launches += launch_lookup(h->tab, d_keys, U, true, slot, u_w, u_vrow, h->u_wv.as<int2>(), s);
+    h->launches += launch_lookup(h->tab, d_keys, U, dU, insert, slot, u_w, u_vrow, h->u_wv.as<int2>(), s);
   }
   }
   FmView v;
@@ -313,6 +236,8 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   v.wbase = u_w; v.w_pos = nullptr;
   v.wv = h->u_wv.as<int2>();
   v.vbase = h->tab.V; v.v_pos = u_vrow; v.vstride = h->tab.rs; v.dense = 0;
+  v.l2hint = h->l2_hints;
+  if (dU && !(sorted || !is_train)) return h->fail(DFB_ERR_INVALID, "device-side key count needs the sorted path");
   if (sorted) {
     DFB_TRY(ensure_sorted_ws(h, nrows, nnz, U, d_val != nullptr, csc_ready));
   } else if (is_train) {
@@ -378,22 +303,22 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   }
   StageTimer tm_upd(h, 4);
   if (sorted) {
-    int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U,
+    int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U, dU,
                                csc ? csc->col_start.as<int>() : h->col_start.as<int>(),
                                csc ? csc->col_end.as<int>() : h->col_end.as<int>(),
                                csc ? csc->occ_sorted.p : h->occ_sorted.p, d_val != nullptr, h->p_row.as<float>(),
-                               h->pxv.as<float>(), flags, 1, s);
+                               h->pxv.as<float>(), flags, 1, nullptr, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
     h->launches += nl;
-    h->launches += launch_initv(h->tab, h->prm, slot, U, flags, pos, h->cub.p, h->cub.bytes, s);
+    h->launches += launch_initv(h->tab, h->prm, slot, U, dU, flags, pos, s);
   } else if (is_train) {
     // Push(kGradient): FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
     h->launches += launch_update_dense(h->tab, h->prm, slot, u_vrow, 0, U, h->gw.as<float>(),
                                        d_val ? h->gxxp.as<float>() : nullptr, h->gV.as<float>(), flags, 1,
                                        d_val ? 1 : 2, s);
-    h->launches += launch_initv(h->tab, h->prm, slot, U, flags, pos, h->cub.p, h->cub.bytes, s);
+    h->launches += launch_initv(h->tab, h->prm, slot, U, nullptr, flags, pos, s);
   } else {
-    h->launches += launch_penalty(h->prm, h->tab.prog, u_w, u_vrow, h->tab.V, h->tab.rs, 0, U, s);
+    h->launches += launch_penalty(h->prm, h->tab.prog, u_w, u_vrow, h->tab.V, h->tab.rs, 0, U, dU, s);
   }
   if (h->profile) {
     tm_upd.~StageTimer(); tm_upd.e = nullptr;
@@ -404,20 +329,38 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   return 0;
 }
 
+}  // namespace
+
 // fold the oldest outstanding snapshot of the pipelined path into *acc
-int collect_one(dfb_engine* h, DevProgress* acc) {
+int dfbh::collect_one(dfb_engine* h, DevProgress* acc) {
   const int r = (int)(h->collected % dfb_engine::kRing);
   DFB_CUDA(h, cudaEventSynchronize(h->ring_done[r]));
   add_prog(*acc, h->h_ring[r]);
   h->collected++;
   return 0;
 }
+using dfbh::collect_one;
 
-// Localizer::Compact on the device.  Leaves keys in l_keys, the remapped CSR index in l_lidx and the CSC
-// view in occ_sorted / col_start / col_end; returns the number of unique keys (two small D2H syncs:
-// the significant key-bit range for the radix sort, then the unique count).
-int localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
-                 const float* d_val, uint64_t max_index, dfb_engine::LocSet& L, cudaStream_t s, size_t* U_out) {
+namespace {
+int lowest_bit(unsigned long long or_all) {
+  if (!or_all) return 63;    // every key is 0
+  int b = 0;
+  while (((or_all >> b) & 1ULL) == 0) ++b;
+  return b;
+}
+}  // namespace
+
+// Localizer::Compact on the device.  Leaves the unique keys, the remapped CSR index and the CSC view
+// (occ_sorted / col_start / col_end; col_start has U+1 entries) in L.  The radix sort only visits the key
+// bits that are not constant zero; which bits those are is either given (id_bits: ids < 2^id_bits fill the
+// top nibbles of the reversed key), or learned: the first batch is measured with one 8-byte D2H sync, later
+// batches reuse the range (verified on the device; earlier batches' OR masks are read back without waiting
+// and can only widen it); exact_range measures every batch (the synchronous entry points, which wait for
+// the step anyway).  With need_host_U the unique-key count is also synchronised to the host, otherwise it
+// stays on the device (L.dU()) and *U_out is the capacity nnz.
+int dfbh::localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
+                       const float* d_val, uint64_t max_index, dfb_engine::LocSet& L, cudaStream_t s,
+                       bool need_host_U, bool exact_range, size_t* U_out) {
   *U_out = 0;
   if (nnz > 0x7fffffffULL) return h->fail(DFB_ERR_INVALID, "batch too large");   // localizer.cc:19-20
   if (max_index == 0) return h->fail(DFB_ERR_INVALID, "max_index must be > 0");
@@ -429,69 +372,109 @@ int localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off,
   DFB_TRY(h->ensure(h->l_head, n1 * 4));
   DFB_TRY(h->ensure(h->l_rank, n1 * 4));
   DFB_TRY(h->ensure(h->l_nnzrow, n1 * 4));
-  DFB_TRY(h->ensure(h->l_scal, 16));
   DFB_TRY(h->ensure(h->l_tmp, localize_sort_tmp_bytes(nnz)));
+  DFB_TRY(h->ensure(L.scal, 16));
   DFB_TRY(h->ensure(L.keys, n1 * 8));
   DFB_TRY(h->ensure(L.lidx, n1 * 4));
   DFB_TRY(h->ensure(L.cnt, n1 * 4));
   DFB_TRY(h->ensure(L.occ_sorted, n1 * (d_val ? 8 : 4)));
-  DFB_TRY(h->ensure(L.col_start, n1 * 4));
+  DFB_TRY(h->ensure(L.col_start, (n1 + 1) * 4));
   DFB_TRY(h->ensure(L.col_end, n1 * 4));
-  if (nnz == 0) return 0;
-  unsigned long long* scal = h->l_scal.as<unsigned long long>();
+  unsigned long long* scal = L.scal.as<unsigned long long>();
+  if (nnz == 0) {
+    DFB_CUDA(h, cudaMemsetAsync(scal, 0, 16, s));
+    return 0;
+  }
   h->launches += launch_localize_keys(d_ids, nnz, max_index, h->l_rkeys.as<unsigned long long>(),
                                       h->l_pos.as<uint32_t>(), scal, d_off, nrows, h->l_nnzrow.as<uint32_t>(), s);
-  DFB_CUDA(h, cudaMemcpyAsync(h->h_scal, scal, 8, cudaMemcpyDeviceToHost, s));
-  DFB_CUDA(h, cudaStreamSynchronize(s));
-  const unsigned long long or_all = h->h_scal[0];
-  int begin_bit = 0;
-  if (or_all) { while (((or_all >> begin_bit) & 1ULL) == 0) ++begin_bit; }
-  else begin_bit = 63;    // every key is 0
+  // ---- the bit range of the sort ----
+  int begin_bit = -1;
+  const bool restricted = max_index != ~0ULL;        // Localizer(max_index) of dfb_localize: range unknown
+  if (h->id_bits > 0 && !restricted) {
+    begin_bit = 64 - 4 * ((h->id_bits + 3) / 4);
+  } else if (!restricted && !need_host_U && !exact_range) {
+    for (int q = 0; q < 2; ++q)                        // masks of earlier batches, if they have arrived
+      if (h->or_pending[q] && cudaEventQuery(h->ev_or[q]) == cudaSuccess) {
+        h->or_pending[q] = false;
+        const int b = lowest_bit(h->h_or[q]);
+        if (h->loc_begin_bit < 0 || b < h->loc_begin_bit) h->loc_begin_bit = b;
+      }
+    begin_bit = h->loc_begin_bit;
+  }
+  if (begin_bit < 0) {
+    DFB_CUDA(h, cudaMemcpyAsync(h->h_scal, scal, 8, cudaMemcpyDeviceToHost, s));
+    DFB_CUDA(h, cudaStreamSynchronize(s));
+    begin_bit = lowest_bit(h->h_scal[0]);
+    if (!restricted && (h->loc_begin_bit < 0 || begin_bit < h->loc_begin_bit)) h->loc_begin_bit = begin_bit;
+  } else if (h->id_bits <= 0 && !restricted) {
+    const int q = (int)(h->or_seq++ & 1);
+    if (!h->or_pending[q]) {
+      DFB_CUDA(h, cudaMemcpyAsync(h->h_or + q, scal, 8, cudaMemcpyDeviceToHost, s));
+      DFB_CUDA(h, cudaEventRecord(h->ev_or[q], s));
+      h->or_pending[q] = true;
+    }
+  }
   h->launches += launch_localize_sort(h->l_rkeys.as<unsigned long long>(), h->l_pos.as<uint32_t>(), nnz, begin_bit,
                                       h->l_skeys.as<unsigned long long>(), h->l_spos.as<uint32_t>(),
                                       h->l_head.as<int>(), h->l_rank.as<int>(), h->l_tmp.p, h->l_tmp.bytes,
                                       h->l_nnzrow.as<uint32_t>(), d_val, L.keys.as<uint64_t>(),
                                       L.col_start.as<int>(), L.col_end.as<int>(), L.lidx.as<uint32_t>(),
-                                      L.occ_sorted.p, scal + 1, s);
-  DFB_CUDA(h, cudaMemcpyAsync(h->h_scal + 1, scal + 1, 8, cudaMemcpyDeviceToHost, s));
-  DFB_CUDA(h, cudaStreamSynchronize(s));
-  *U_out = (size_t)h->h_scal[1];
+                                      L.occ_sorted.p, scal, h->tab.prog, s);
+  if (need_host_U) {
+    DFB_CUDA(h, cudaMemcpyAsync(h->h_scal + 1, scal + 1, 8, cudaMemcpyDeviceToHost, s));
+    DFB_CUDA(h, cudaStreamSynchronize(s));
+    *U_out = (size_t)h->h_scal[1];
+  } else {
+    *U_out = nnz;
+  }
   return 0;
 }
+using dfbh::localize_dev;
+
+namespace {
 
 // raw (un-localized) CSR<u64> minibatch: Localizer::Compact + the fused step, all on the device.
-// The localizer runs on its own stream into one of two output sets, so while the host waits for
-// the two 8-byte results of batch t+1 the main stream is still busy with the step of batch t.
+// The localizer runs on its own stream into one of two output sets, overlapped with the step of the
+// previous batch; on the sorted fast path nothing of it is synchronised to the host (the unique-key
+// count stays on the device), so a step is one uninterrupted enqueue.
 int step_raw_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
-                 const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready) {
+                 const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready,
+                 bool exact_range = false) {
   dfb_engine::LocSet& L = h->loc[h->loc_seq & 1];
   cudaStream_t ls = h->loc_stream;
   if (inputs_ready) DFB_CUDA(h, cudaStreamWaitEvent(ls, inputs_ready, 0));
   if (L.used) DFB_CUDA(h, cudaStreamWaitEvent(ls, L.consumed, 0));
+  const bool dev_count_ok = !h->force_generic && fm_fast_supported(h->prm.V_dim) && (!is_train || h->scatter_sorted);
   size_t U = 0;
-  DFB_TRY(localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, L, ls, &U));   // Localizer(-1, ...), sgd_learner.cc:203
+  DFB_TRY(localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, L, ls, !dev_count_ok, exact_range, &U));   // Localizer(-1, ...), sgd_learner.cc:203
   const float* d_cnt = nullptr;
+  const int* cnt_cols = nullptr;
   if (push_cnt && U) {
-    h->launches += launch_cnt_from_cols(L.col_start.as<int>(), L.col_end.as<int>(), U, L.cnt.as<float>(), ls);
-    d_cnt = L.cnt.as<float>();
+    if (dev_count_ok) {
+      cnt_cols = L.col_start.as<int>();       // U+1 column offsets: the counts are their differences
+    } else {
+      h->launches += launch_cnt_from_cols(L.col_start.as<int>(), L.col_end.as<int>(), U, L.cnt.as<float>(), ls);
+      d_cnt = L.cnt.as<float>();
+    }
   }
   DFB_CUDA(h, cudaEventRecord(L.done, ls));
   DFB_CUDA(h, cudaStreamWaitEvent(h->stream, L.done, 0));
   int rc = step_dev(h, nrows, nnz, d_off, L.lidx.as<uint32_t>(), d_val, d_lab, L.keys.as<uint64_t>(), U, d_cnt,
-                    is_train, &L);
+                    is_train, &L, (dev_count_ok && nnz) ? L.dU() : nullptr, cnt_cols);
   DFB_CUDA(h, cudaEventRecord(L.consumed, h->stream));
   L.used = true;
   h->loc_seq++;
   return rc;
 }
 
-int check_csr(dfb_engine* h, size_t nrows, const uint64_t* offset) {
+}  // namespace
+
+int dfbh::check_csr(dfb_engine* h, size_t nrows, const uint64_t* offset) {
   if (nrows && !offset) return h->fail(DFB_ERR_INVALID, "offset is NULL");
   if (nrows && offset[0] != 0) return h->fail(DFB_ERR_INVALID, "offset[0] must be 0 (fm_loss.h:88 assumes it)");
   return 0;
 }
-
-}  // namespace
+using dfbh::check_csr;
 
 extern "C" {
 
@@ -550,6 +533,9 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
       l2_fetch = (int)x;
     }
     else if (k == "overlap_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->overlap_auc = (int)x; }
+    else if (k == "l2_hints") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->l2_hints = (int)x; }
+    else if (k == "id_bits") { if (!need_int(0, 64)) { delete h; return DFB_ERR_PARAM; } h->id_bits = (int)x; }
+    else if (k == "shard_timeout_ms") { if (!need_int(1, 3600000)) { delete h; return DFB_ERR_PARAM; } h->shard_timeout_ms = x; }
     else if (k == "scatter") {
       if (v == "sorted") h->scatter_sorted = 1;
       else if (v == "atomic") h->scatter_sorted = 0;
@@ -606,6 +592,9 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   if ((e = cudaHostAlloc(&h->h_nvals, sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   memset(h->h_prog, 0, sizeof(DevProgress));
   if ((e = cudaHostAlloc(&h->h_scal, 2 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
+  if ((e = cudaHostAlloc(&h->h_or, 2 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
+  for (auto& ev : h->ev_or)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");
   if ((e = cudaHostAlloc(&h->h_ring, dfb_engine::kRing * sizeof(DevProgress), cudaHostAllocDefault)) != cudaSuccess) return cfail("cudaHostAlloc");
   memset(h->h_ring, 0, dfb_engine::kRing * sizeof(DevProgress));
   memset(&h->backlog, 0, sizeof(DevProgress));
@@ -621,15 +610,16 @@ int dfb_destroy(dfb_handle h) {
   if (!h) return DFB_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  if (h->shard) dfbh::shard_destroy(h);
   for (auto& L : h->loc) {
-    DevBuf* lb[] = {&L.keys, &L.lidx, &L.cnt, &L.occ_sorted, &L.col_start, &L.col_end};
+    DevBuf* lb[] = {&L.keys, &L.lidx, &L.cnt, &L.occ_sorted, &L.col_start, &L.col_end, &L.scal};
     for (auto* b : lb) if (b->p) cudaFree(b->p);
     if (L.done) cudaEventDestroy(L.done);
     if (L.consumed) cudaEventDestroy(L.consumed);
   }
   if (h->loc_stream) cudaStreamDestroy(h->loc_stream);
   DevBuf* bufs[] = {&h->u_wv, &h->l_rkeys, &h->l_skeys, &h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow,
-                    &h->l_scal, &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
+                    &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
                     &h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
                     &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
                     &h->a_val, &h->a_lab, &h->a_w, &h->a_wpos, &h->a_vpos, &h->a_pred, &h->a_grad, &h->scal,
@@ -649,6 +639,8 @@ int dfb_destroy(dfb_handle h) {
   if (h->h_nvals) cudaFreeHost(h->h_nvals);
   if (h->h_ring) cudaFreeHost(h->h_ring);
   if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->h_or) cudaFreeHost(h->h_or);
+  for (auto& ev : h->ev_or) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->ring_done) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->pev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -712,9 +704,9 @@ int dfb_push_feacnt(dfb_handle h, const uint64_t* keys, size_t n, const float* c
   DFB_TRY(h2d(h, h->keys, keys, n * sizeof(uint64_t), s));
   DFB_TRY(h2d(h, h->cnt, cnt, n * sizeof(float), s));
   DFB_TRY(ensure_key_ws(h, n));
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
-  h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, h->cnt.as<float>(), h->flags.as<int>(),
-                               h->pos.as<int>(), h->cub.p, h->cub.bytes, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, nullptr, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
+  h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, nullptr, h->cnt.as<float>(), nullptr,
+                               h->flags.as<int>(), h->pos.as<int>(), s);
   return sync_and_check(h);
 }
 
@@ -733,7 +725,7 @@ int dfb_pull(dfb_handle h, const uint64_t* keys, size_t n, float* vals_out, size
   DFB_TRY(ensure_key_ws(h, n));
   if (k == 0) {
     if (vals_cap < n) return h->fail(DFB_ERR_INVALID, "vals_out too small");
-    h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), h->u_w.as<float>(),
+    h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, nullptr, true, h->slot.as<int>(), h->u_w.as<float>(),
                                  h->u_vrow.as<int>(), nullptr, s);
     DFB_CUDA(h, cudaMemcpyAsync(vals_out, h->u_w.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     DFB_TRY(sync_and_check(h));
@@ -746,7 +738,7 @@ int dfb_pull(dfb_handle h, const uint64_t* keys, size_t n, float* vals_out, size
   DFB_TRY(h->ensure(h->lens, n * sizeof(int)));
   DFB_TRY(h->ensure(h->vals, n * (size_t)(k + 1) * sizeof(float)));
   DFB_TRY(h->ensure(h->nvals, sizeof(unsigned long long)));
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, nullptr, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_pack_ragged(h->tab, h->prm, h->slot.as<int>(), n, h->lens.as<int>(), h->pos.as<int>(),
                                     h->vals.as<float>(), h->nvals.as<unsigned long long>(), h->cub.p,
                                     h->cub.bytes, s);
@@ -791,11 +783,10 @@ int dfb_push_grad(dfb_handle h, const uint64_t* keys, size_t n, const float* gra
     d_lens = h->lens.as<int>();
     h->launches += launch_lens_scan(d_lens, n, h->pos.as<int>(), h->cub.p, h->cub.bytes, s);
   }
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, nullptr, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_update_ragged(h->tab, h->prm, h->slot.as<int>(), n, h->vals.as<float>(), d_lens,
                                       h->pos.as<int>(), h->flags.as<int>(), s);
-  h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, h->flags.as<int>(), h->pos.as<int>(),
-                              h->cub.p, h->cub.bytes, s);
+  h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, nullptr, h->flags.as<int>(), h->pos.as<int>(), s);
   return sync_and_check(h);
 }
 
@@ -944,6 +935,7 @@ int dfb_sync(dfb_handle h) {
   DFB_CUDA(h, cudaSetDevice(h->device));
   DFB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
   DFB_CUDA(h, cudaStreamSynchronize(h->loc_stream));
+  if (h->shard) DFB_TRY(dfbh::shard_sync(h));
   DFB_CUDA(h, cudaStreamSynchronize(h->stream));
   return DFB_OK;
 }
@@ -1060,7 +1052,7 @@ int dfb_localize(dfb_handle h, size_t nrows, const uint64_t* offset, const uint6
   size_t U = 0;
   DFB_CUDA(h, cudaStreamSynchronize(h->loc_stream));
   dfb_engine::LocSet& L = h->loc[0];
-  DFB_TRY(localize_dev(h, nrows, nnz, h->a_off.as<uint64_t>(), h->keys.as<uint64_t>(), nullptr, max_index, L, s, &U));
+  DFB_TRY(localize_dev(h, nrows, nnz, h->a_off.as<uint64_t>(), h->keys.as<uint64_t>(), nullptr, max_index, L, s, true, true, &U));
   DFB_CUDA(h, cudaMemcpyAsync(index_out, L.lidx.p, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   DFB_CUDA(h, cudaMemcpyAsync(keys_out, L.keys.p, U * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   if (cnt_out) {
@@ -1080,8 +1072,9 @@ int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_
 }
 
 // H2D of one raw batch into the input set the next submission will use (copy stream)
-static int stage_raw(dfb_handle h, dfb_engine::InSet& in, size_t nrows, size_t nnz, const uint64_t* offset,
-                     const uint64_t* ids, const float* value, const float* label) {
+}  // extern "C"
+int dfbh::stage_raw(dfb_engine* h, dfb_engine::InSet& in, size_t nrows, size_t nnz, const uint64_t* offset,
+                    const uint64_t* ids, const float* value, const float* label) {
   cudaStream_t cs = h->copy_stream;
   if (h->seq >= 2) DFB_CUDA(h, cudaStreamWaitEvent(cs, in.consumed, 0));
   DFB_TRY(h2d(h, in.off, offset, (nrows + 1) * sizeof(uint64_t), cs));
@@ -1091,6 +1084,8 @@ static int stage_raw(dfb_handle h, dfb_engine::InSet& in, size_t nrows, size_t n
   DFB_CUDA(h, cudaEventRecord(in.copied, cs));
   return 0;
 }
+using dfbh::stage_raw;
+extern "C" {
 
 int dfb_prefetch_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids, const float* value,
                      const float* label) {
@@ -1106,8 +1101,8 @@ int dfb_prefetch_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const u
   return DFB_OK;
 }
 
-int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
-                             const float* value, const float* label, int push_cnt, int is_train) {
+static int raw_async_impl(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                          const float* value, const float* label, int push_cnt, int is_train, bool exact_range) {
   if (!h) return DFB_ERR_INVALID;
   DFB_TRY(check_csr(h, nrows, offset));
   if (nrows && !label) return h->fail(DFB_ERR_INVALID, "label is NULL");
@@ -1120,17 +1115,23 @@ int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset,
   in.pre_ids = nullptr;
   DFB_CUDA(h, cudaStreamWaitEvent(h->stream, in.copied, 0));
   int rc = step_raw_dev(h, nrows, nnz, in.off.as<uint64_t>(), in.ids.as<uint64_t>(),
-                        value ? in.val.as<float>() : nullptr, in.lab.as<float>(), push_cnt, is_train, in.copied);
+                        value ? in.val.as<float>() : nullptr, in.lab.as<float>(), push_cnt, is_train, in.copied,
+                        exact_range);
   DFB_CUDA(h, cudaEventRecord(in.consumed, h->stream));
   h->seq++;
   if (rc != 0) return rc;
   return snapshot_step(h);
 }
 
+int dfb_train_step_raw_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                             const float* value, const float* label, int push_cnt, int is_train) {
+  return raw_async_impl(h, nrows, offset, ids, value, label, push_cnt, is_train, false);
+}
+
 int dfb_train_step_raw(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids, const float* value,
                        const float* label, int push_cnt, int is_train, dfb_progress* out, float* pred_out) {
   if (!h) return DFB_ERR_INVALID;
-  DFB_TRY(dfb_train_step_raw_async(h, nrows, offset, ids, value, label, push_cnt, is_train));
+  DFB_TRY(raw_async_impl(h, nrows, offset, ids, value, label, push_cnt, is_train, true));
   if (pred_out && nrows)
     DFB_CUDA(h, cudaMemcpyAsync(pred_out, h->pred.p, nrows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   return dfb_read_progress(h, out);
@@ -1291,7 +1292,7 @@ int dfb_read_entries(dfb_handle h, const uint64_t* keys, size_t n, float* scal_o
   DFB_TRY(h->ensure(h->rcg, n * (size_t)(k ? k : 1) * sizeof(float)));
   DFB_CUDA(h, cudaMemsetAsync(h->rV.p, 0, n * (size_t)(k ? k : 1) * sizeof(float), s));
   DFB_CUDA(h, cudaMemsetAsync(h->rcg.p, 0, n * (size_t)(k ? k : 1) * sizeof(float), s));
-  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, false, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, h->keys.as<uint64_t>(), n, nullptr, false, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_read_entries(h->tab, h->slot.as<int>(), n, h->scal.as<float>(), h->hasv.as<int>(),
                                      h->rV.as<float>(), h->rcg.as<float>(), k, s);
   DFB_CUDA(h, cudaMemcpyAsync(scal_out, h->scal.p, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1336,9 +1337,9 @@ int dfb_dev_feacnt(dfb_handle h, const uint64_t* d_keys, size_t n, const float* 
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
-  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
-  h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, d_cnt, h->flags.as<int>(), h->pos.as<int>(),
-                               h->cub.p, h->cub.bytes, s);
+  h->launches += launch_lookup(h->tab, d_keys, n, nullptr, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
+  h->launches += launch_feacnt(h->tab, h->prm, h->slot.as<int>(), n, nullptr, d_cnt, nullptr, h->flags.as<int>(),
+                               h->pos.as<int>(), s);
   DFB_CUDA(h, cudaGetLastError());
   return DFB_OK;
 }
@@ -1350,7 +1351,7 @@ static int dev_pull_rows_impl(dfb_handle h, const uint64_t* d_keys, size_t n, fl
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
-  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, d_keys, n, nullptr, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   h->launches += launch_gather_rows(h->tab, h->slot.as<int>(), n, d_w_out, d_hasv_out, d_hasv_out2,
                                     h->prm.V_dim > 0 ? d_V_out : nullptr, s);
   DFB_CUDA(h, cudaGetLastError());
@@ -1503,7 +1504,7 @@ static int dev_fm_step_impl(dfb_handle h, size_t nrows, size_t nnz, const uint64
                               h->auc_v.as<float>(), h->auc_tmp.p, h->auc_tmp.bytes, &h->tab.prog->auc, s);
   }
   // the worker evaluates the penalty of what it pulled (sgd_learner.cc:148)
-  if (!sorted) h->launches += launch_penalty(h->prm, h->tab.prog, d_w, d_hasv, d_V, ks, 1, nkeys, s);
+  if (!sorted) h->launches += launch_penalty(h->prm, h->tab.prog, d_w, d_hasv, d_V, ks, 1, nkeys, nullptr, s);
   DFB_CUDA(h, cudaGetLastError());
   return DFB_OK;
 }
@@ -1515,15 +1516,14 @@ int dfb_dev_push_rows(dfb_handle h, const uint64_t* d_keys, size_t n, const floa
   if (n == 0) return DFB_OK;
   DFB_TRY(ensure_key_ws(h, n));
   cudaStream_t s = h->stream;
-  h->launches += launch_lookup(h->tab, d_keys, n, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
+  h->launches += launch_lookup(h->tab, d_keys, n, nullptr, true, h->slot.as<int>(), nullptr, nullptr, nullptr, s);
   int nl = h->force_generic ? -1 : launch_update_pushed(h->tab, h->prm, h->slot.as<int>(), d_hasv, n, d_gw, d_gV,
                                                         h->flags.as<int>(), s);
   if (nl < 0)
     nl = launch_update_dense(h->tab, h->prm, h->slot.as<int>(), d_hasv, 1, n, d_gw, nullptr, d_gV,
                              h->flags.as<int>(), 0, 0, s);
   h->launches += nl;
-  h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, h->flags.as<int>(), h->pos.as<int>(),
-                              h->cub.p, h->cub.bytes, s);
+  h->launches += launch_initv(h->tab, h->prm, h->slot.as<int>(), n, nullptr, h->flags.as<int>(), h->pos.as<int>(), s);
   DFB_CUDA(h, cudaGetLastError());
   return DFB_OK;
 }

@@ -1,0 +1,125 @@
+// difacto_b200/csrc/engine_internal.cuh -- the engine object behind a dfb_handle and the host-side helpers
+// shared by engine.cu (C-ABI, single-GPU step) and shard.cu (the NVLink-sharded store).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/difacto_b200.h"
+#include "dfb_internal.cuh"
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct ShardState;   // shard.cu
+
+struct dfb_engine {
+  dfb::Params prm;
+  int device = 0;
+  int compute_auc = 1;
+  int force_generic = 0;
+  int scatter_sorted = 1;   // 1: atomic-free sorted reduction (deterministic); 0: red.global atomics
+  int overlap_auc = 1;      // run the AUC kernels on the auxiliary stream, concurrently with the update
+  int has_aux = 1;          // false after restoring a snapshot saved without aux data (sgd_updater.h:88)
+  int l2_hints = 1;         // per-load L2 eviction policies in the gather kernels
+  int id_bits = 0;          // > 0: feature ids are < 2^id_bits (fixes the radix-sort bit range of the GPU localizer)
+  int loc_begin_bit = -1;   // auto mode: lowest significant bit of the reversed keys seen so far (sticky)
+  long long shard_timeout_ms = 20000;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_fm_done = nullptr, ev_auc_done = nullptr;
+  dfb::Table tab;
+  std::string err;
+  std::vector<std::pair<std::string, std::string>> unknown;
+  uint64_t launches = 0;
+
+  // workspaces (grown on demand)
+  DevBuf u_wv;
+  DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
+  DevBuf auc_k, auc_v, auc_tmp;
+  DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
+  DevBuf l_rkeys, l_skeys, l_pos, l_spos, l_head, l_rank, l_nnzrow, l_tmp;
+  // outputs of the GPU localizer, double-buffered: the localizer of batch t+1 runs on loc_stream
+  // while the step of batch t (which reads set t) runs on the main stream
+  struct LocSet {
+    DevBuf keys, lidx, cnt, occ_sorted, col_start, col_end;
+    DevBuf scal;                          // {OR of all reversed keys, number of unique keys} (u64 x 2)
+    cudaEvent_t done = nullptr, consumed = nullptr;
+    bool used = false;
+    const unsigned long long* dU() const { return scal.as<unsigned long long>() + 1; }
+  } loc[2];
+  uint64_t loc_seq = 0;
+  cudaStream_t loc_stream = nullptr;
+  unsigned long long* h_scal = nullptr;   // pinned: {or_all, n_unique} of a synchronous localize
+  unsigned long long* h_or = nullptr;     // pinned ring [2]: or_all of earlier asynchronous localizes
+  cudaEvent_t ev_or[2] = {nullptr, nullptr};
+  bool or_pending[2] = {false, false};
+  uint64_t or_seq = 0;
+  DevBuf a_off, a_idx, a_val, a_lab, a_w, a_wpos, a_vpos, a_pred, a_grad;
+  DevBuf scal, hasv, rV, rcg, nvals;
+  // double-buffered inputs of the pipelined step
+  struct InSet {
+    DevBuf off, idx, val, lab, keys, cnt, ids;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+    const void* pre_ids = nullptr;     // host batch already staged by dfb_prefetch_raw (identity check)
+    size_t pre_nrows = 0, pre_nnz = 0;
+  } in[2];
+  uint64_t seq = 0;
+  // per-step Progress snapshots of the pipelined path (pinned ring + completion events)
+  static constexpr int kRing = 8;
+  dfb::DevProgress* h_ring = nullptr;
+  cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t submitted = 0, collected = 0;
+  dfb::DevProgress backlog;             // snapshots folded in when the ring was full
+  // optional per-stage CUDA-event timing (bench.py's roofline numbers)
+  static constexpr int kStages = 5;      // lookup+pull, fm, auc, csc sort, update(+initv)
+  static constexpr int kProfRing = 32;
+  int profile = 0;
+  std::vector<cudaEvent_t> pev;          // [kProfRing][kStages][2]
+  std::vector<char> pev_used;            // [kProfRing][kStages]
+  uint64_t prof_steps = 0;
+  double stage_ms[kStages] = {0, 0, 0, 0, 0};
+  uint64_t stage_n[kStages] = {0, 0, 0, 0, 0};
+  dfb::DevProgress* h_prog = nullptr;   // pinned
+  unsigned long long* h_nvals = nullptr;  // pinned
+  ShardState* shard = nullptr;          // the NVLink-sharded store this engine is a rank of (shard.cu)
+
+  int fail(int code, const std::string& msg) { err = msg; return code; }
+  int cuda_fail(cudaError_t e, const char* what) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return DFB_ERR_CUDA;
+  }
+  // grow a workspace; frees/reallocs only after the streams that may still read it have drained
+  int ensure(DevBuf& b, size_t bytes);
+};
+
+#define DFB_CUDA(h, call)                                                  \
+  do {                                                                     \
+    cudaError_t _e = (call);                                               \
+    if (_e != cudaSuccess) return (h)->cuda_fail(_e, #call);               \
+  } while (0)
+#define DFB_TRY(expr)              \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != 0) return _rc;      \
+  } while (0)
+
+// host-side helpers defined in engine.cu and used by shard.cu
+namespace dfbh {
+int ensure_key_ws(dfb_engine* h, size_t n);
+// Localizer::Compact on the device into L (no host synchronisation unless need_host_U):
+//   *U_out = the unique-key count when need_host_U, else the capacity (nnz); L.dU() holds the count on the device
+int localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
+                 const float* d_val, uint64_t max_index, dfb_engine::LocSet& L, cudaStream_t s, bool need_host_U,
+                 bool exact_range, size_t* U_out);
+int check_csr(dfb_engine* h, size_t nrows, const uint64_t* offset);
+int stage_raw(dfb_engine* h, dfb_engine::InSet& in, size_t nrows, size_t nnz, const uint64_t* offset,
+              const uint64_t* ids, const float* value, const float* label);
+int collect_one(dfb_engine* h, dfb::DevProgress* acc);
+void shard_destroy(dfb_engine* h);      // shard.cu
+int shard_sync(dfb_engine* h);          // shard.cu: drain the shard's streams
+}  // namespace dfbh

@@ -18,6 +18,7 @@
 #include "dfb_internal.cuh"
 
 #include <math.h>
+#include <string.h>
 
 namespace dfb {
 
@@ -27,6 +28,27 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float4 ldg128(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// per-load L2 eviction policies (createpolicy + ld.global.nc.L2::cache_hint)
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 normal, 1 evict_first, 2 evict_last
+  uint64_t pol;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg128_pol(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int2 ldg64_pol(const int2* p, uint64_t pol) {
+  int2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
 }
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -80,11 +102,13 @@ __device__ __forceinline__ void block_add_loss(float loss_acc, size_t nrows, Dev
 // MODE 0: predict only.  MODE 1: training with fp32 red.global scatter into dense gradient rows.
 // MODE 2: training, "emit": writes p_i, p_i*XV_i and the (row[,x]) payload of every nnz so that
 //         the gradient can be reduced per key without atomics (kernels_table.cu: k_bwd_update).
+// MODE 3: owner side of the fused sharded store: partial sums of every worker's rows over this owner's
+//         key segment, stored into the workers' mailboxes (see PartArgs).
 #ifndef DFB_FM_MINBLOCKS
 #define DFB_FM_MINBLOCKS 4
 #endif
 template <int K, int MODE, bool HAS_VAL>
-__global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, FmView v) {
+__global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, FmView v, PartArgs pa) {
   constexpr bool TRAIN = MODE == 1;
   constexpr int LPR = K / 4;                 // lanes per V row, one float4 each
   constexpr int G = 32 / LPR;                // V rows fetched by one warp-wide load
@@ -94,9 +118,25 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   float loss_acc = 0.f;
+  const uint64_t pol_v = l2_policy(v.l2hint ? 1 : 0), pol_wv = l2_policy(v.l2hint ? 2 : 0);
+  const size_t total_rows = MODE == 3 ? (size_t)pa.nsrc * (size_t)pa.bcap : b.nrows;
 
-  for (size_t row = warp0; row < b.nrows; row += nwarps) {
-    const uint64_t o0 = b.offset[row], o1 = b.offset[row + 1];
+  for (size_t vrow_id = warp0; vrow_id < total_rows; vrow_id += nwarps) {
+    size_t row = vrow_id;
+    const uint64_t* offp = b.offset;
+    const uint32_t* idxp = b.index;
+    const float* valp = b.value;
+    const int2* wvp = v.wv;
+    int src = 0;
+    if (MODE == 3) {
+      const int s0 = (int)(vrow_id / pa.bcap);
+      row = vrow_id - (size_t)s0 * pa.bcap;
+      src = s0 + pa.rot;
+      if (src >= pa.nsrc) src -= pa.nsrc;
+      if (row >= (size_t)shard_hdr_nrows(pa.s[src].hdr)) continue;
+      offp = pa.s[src].rowptr; idxp = pa.s[src].ridx; valp = pa.s[src].rval; wvp = pa.s[src].wv;
+    }
+    const uint64_t o0 = offp[row], o1 = offp[row + 1];
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     float acc2 = 0.f, wsum = 0.f;
 
@@ -107,10 +147,10 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
       float x = 0.f, w = 0.f;
       int vr = -1;
       if (valid) {
-        u = __ldg(b.index + j);
-        x = HAS_VAL ? __ldg(b.value + j) : 1.f;
-        if (v.wv) {
-          const int2 t = __ldg(v.wv + u);
+        u = __ldg(idxp + j);
+        x = HAS_VAL ? __ldg(valp + j) : 1.f;
+        if (wvp) {
+          const int2 t = ldg64_pol(wvp + u, pol_wv);
           w = __int_as_float(t.x);
           vr = t.y;
         } else {
@@ -136,7 +176,7 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
           const float x_t = __shfl_sync(kFull, x, t & 31);
           const bool ok = (t < cnt) && (vr_t >= 0);
           xs[q] = ok ? x_t : 0.f;
-          vv[q] = ok ? ldg128(v.vbase + (long long)vr_t * v.vstride + sub * 4)
+          vv[q] = ok ? ldg128_pol(v.vbase + (long long)vr_t * v.vstride + sub * 4, pol_v)
                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
@@ -157,10 +197,16 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
       xv.z += __shfl_xor_sync(kFull, xv.z, o);
       xv.w += __shfl_xor_sync(kFull, xv.w, o);
     }
-    float s1 = grp == 0 ? (xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w) : 0.f;
-    s1 = warp_sum(s1);
     acc2 = warp_sum(acc2);
     wsum = warp_sum(wsum);
+    if (MODE == 3) {
+      // ||XV||^2 is not linear in the rows: the worker squares the SUM of the owners' partials
+      if (grp == 0) *reinterpret_cast<float4*>(pa.s[src].out_xv + row * (size_t)K + sub * 4) = xv;
+      if (lane == 0) pa.s[src].out_sc[row] = make_float2(acc2, wsum);
+      continue;
+    }
+    float s1 = grp == 0 ? (xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w) : 0.f;
+    s1 = warp_sum(s1);
     float pred = (b.pred_acc ? b.pred_io[row] : 0.f) + wsum;
     pred += 0.5f * (s1 - acc2);
     pred = pred > 20.f ? 20.f : (pred < -20.f ? -20.f : pred);   // fm_loss.h:118
@@ -210,7 +256,7 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
       }
     }
   }
-  block_add_loss(loss_acc, b.nrows, b.prog);
+  if (MODE != 3) block_add_loss(loss_acc, b.nrows, b.prog);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -350,22 +396,46 @@ int launch_fast_k(const FmBatch& b, const FmView& v, cudaStream_t s) {
   size_t need = (b.nrows + 7) / 8;
   int grid = (int)(need < (size_t)(148 * 8) ? (need ? need : 1) : (size_t)(148 * 8));
   const bool hv = b.value != nullptr;
+  PartArgs pa;
+  memset(&pa, 0, sizeof(pa));
   if (b.train && b.emit) {
-    if (hv) k_fm_fast<K, 2, true><<<grid, threads, 0, s>>>(b, v);
-    else    k_fm_fast<K, 2, false><<<grid, threads, 0, s>>>(b, v);
+    if (hv) k_fm_fast<K, 2, true><<<grid, threads, 0, s>>>(b, v, pa);
+    else    k_fm_fast<K, 2, false><<<grid, threads, 0, s>>>(b, v, pa);
   } else if (b.train) {
-    if (hv) k_fm_fast<K, 1, true><<<grid, threads, 0, s>>>(b, v);
-    else    k_fm_fast<K, 1, false><<<grid, threads, 0, s>>>(b, v);
+    if (hv) k_fm_fast<K, 1, true><<<grid, threads, 0, s>>>(b, v, pa);
+    else    k_fm_fast<K, 1, false><<<grid, threads, 0, s>>>(b, v, pa);
   } else {
-    if (hv) k_fm_fast<K, 0, true><<<grid, threads, 0, s>>>(b, v);
-    else    k_fm_fast<K, 0, false><<<grid, threads, 0, s>>>(b, v);
+    if (hv) k_fm_fast<K, 0, true><<<grid, threads, 0, s>>>(b, v, pa);
+    else    k_fm_fast<K, 0, false><<<grid, threads, 0, s>>>(b, v, pa);
   }
+  return 1;
+}
+
+template <int K>
+int launch_partial_k(bool valued, const FmView& v, const PartArgs& pa, cudaStream_t s) {
+  FmBatch b;
+  memset(&b, 0, sizeof(b));
+  b.V_dim = K;
+  const int grid = 148 * 8;
+  if (valued) k_fm_fast<K, 3, true><<<grid, 256, 0, s>>>(b, v, pa);
+  else        k_fm_fast<K, 3, false><<<grid, 256, 0, s>>>(b, v, pa);
   return 1;
 }
 
 }  // namespace
 
 bool fm_fast_supported(int k) { return k == 8 || k == 16 || k == 32 || k == 64 || k == 128; }
+
+int launch_fm_partial(int V_dim, bool valued, const FmView& v, const PartArgs& pa, cudaStream_t s) {
+  switch (V_dim) {
+    case 8: return launch_partial_k<8>(valued, v, pa, s);
+    case 16: return launch_partial_k<16>(valued, v, pa, s);
+    case 32: return launch_partial_k<32>(valued, v, pa, s);
+    case 64: return launch_partial_k<64>(valued, v, pa, s);
+    case 128: return launch_partial_k<128>(valued, v, pa, s);
+  }
+  return -1;
+}
 
 int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t s) {
   const int k = b.V_dim;

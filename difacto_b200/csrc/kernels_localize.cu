@@ -9,7 +9,7 @@
 //
 // The same sort also yields the CSC view of the batch (per key: the rows that contain it, in row
 // order) that the atomic-free gradient kernel needs, so a raw-id step skips the separate CSC sort.
-#include "dfb_internal.cuh"
+#include "dfb_device.cuh"
 
 #include <cub/cub.cuh>
 
@@ -74,7 +74,8 @@ __global__ void k_emit(const unsigned long long* __restrict__ skeys, const uint3
                        const uint32_t* __restrict__ nnz_row, const float* __restrict__ value,
                        uint64_t* __restrict__ keys_out, int* __restrict__ col_start, int* __restrict__ col_end,
                        uint32_t* __restrict__ lidx_out, uint32_t* __restrict__ occ_row,
-                       unsigned long long* __restrict__ occ_rowx, unsigned long long* __restrict__ n_unique) {
+                       unsigned long long* __restrict__ occ_rowx, unsigned long long* __restrict__ scal,
+                       int begin_bit, DevProgress* prog) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int r = rank1[j] - 1;
@@ -90,7 +91,17 @@ __global__ void k_emit(const unsigned long long* __restrict__ skeys, const uint3
   }
   if (j == n - 1) {
     col_end[r] = (int)n;
-    *n_unique = (unsigned long long)(r + 1);
+    col_start[r + 1] = (int)n;      // col_start doubles as the U+1 column offsets of the CSC view
+    // scal = {OR of all keys, number of unique keys}.  A key bit below the sorted range means the range was
+    // assumed too narrow (id_bits / the range learned from earlier batches): the batch is NOT sorted, so it is
+    // dropped (zero keys) and the error is reported instead of training on garbage.
+    const unsigned long long low = begin_bit > 0 ? (scal[0] & ((1ULL << begin_bit) - 1ULL)) : 0ULL;
+    if (low != 0ULL) {
+      scal[1] = 0ULL;
+      if (prog) raise_err(prog, DFB_ERR_INVALID);
+    } else {
+      scal[1] = (unsigned long long)(r + 1);
+    }
   }
 }
 
@@ -126,9 +137,9 @@ int launch_localize_keys(const uint64_t* ids, size_t nnz, uint64_t max_index, un
 int launch_localize_sort(const unsigned long long* rkeys, const uint32_t* pos, size_t nnz, int begin_bit,
                          unsigned long long* skeys, uint32_t* spos, int* head, int* rank1, void* tmp, size_t tmp_bytes,
                          const uint32_t* nnz_row, const float* value, uint64_t* keys_out, int* col_start,
-                         int* col_end, uint32_t* lidx_out, void* occ_sorted, unsigned long long* n_unique,
-                         cudaStream_t s) {
-  cudaMemsetAsync(n_unique, 0, sizeof(unsigned long long), s);
+                         int* col_end, uint32_t* lidx_out, void* occ_sorted, unsigned long long* scal,
+                         DevProgress* prog, cudaStream_t s) {
+  cudaMemsetAsync(scal + 1, 0, sizeof(unsigned long long), s);
   if (nnz == 0) return 0;
   cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, rkeys, skeys, pos, spos, (int)nnz, begin_bit, 64, s);
   const int grid = (int)((nnz + 255) / 256);
@@ -136,7 +147,7 @@ int launch_localize_sort(const unsigned long long* rkeys, const uint32_t* pos, s
   cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, head, rank1, (int)nnz, s);
   k_emit<<<grid, 256, 0, s>>>(skeys, spos, head, rank1, nnz, nnz_row, value, keys_out, col_start, col_end, lidx_out,
                               reinterpret_cast<uint32_t*>(occ_sorted),
-                              reinterpret_cast<unsigned long long*>(occ_sorted), n_unique);
+                              reinterpret_cast<unsigned long long*>(occ_sorted), scal, begin_bit, prog);
   return 5 + (64 - begin_bit + 7) / 8;
 }
 

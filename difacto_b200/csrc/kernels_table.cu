@@ -12,32 +12,19 @@
 //                       rows consume the random stream in ascending key order like the reference
 // plus Loss::Evaluate (loss.h:57-66), BinClassMetric::AUC (bin_class_metric.h:35-56) and
 // SGDLearner::EvaluatePenalty (sgd_learner.cc:249-273).
-#include "dfb_internal.cuh"
+#include "dfb_device.cuh"
 
 #include <cub/cub.cuh>
-
-#include "../../include/difacto_b200.h"
 
 namespace dfb {
 
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned kFull = kFullMask;
 
-__device__ __forceinline__ uint64_t hash64(uint64_t h) {
-  h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
-  h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
-  h ^= h >> 33;
-  return h;
-}
+__device__ __forceinline__ float warp_sum(float v) { return warp_sum_f(v); }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
-
-__device__ __forceinline__ void raise(DevProgress* prog, int code) { atomicCAS(&prog->err, 0, code); }
+__device__ __forceinline__ void raise(DevProgress* prog, int code) { raise_err(prog, code); }
 
 __global__ void k_table_init(Entry* tab, uint64_t cap, TableState* st, DevProgress* prog, unsigned seed) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,66 +42,84 @@ __global__ void k_table_init(Entry* tab, uint64_t cap, TableState* st, DevProgre
   }
 }
 
-// model_[key] (sgd_updater.cc:43-45,65-67,86-88): find or default-construct
+// model_[key] (sgd_updater.cc:43-45,65-67,86-88): find or default-construct, and the Pull of the
+// fused path (w and the V-row index of every key).  Random 32-byte sectors: the kernel is latency
+// bound, so every thread keeps ILP independent first probes in flight (both halves of the entry are
+// fetched with the probe; a hit needs no second round trip) and only collisions fall back to the
+// serial probe loop.
 template <bool INSERT>
-__global__ void k_lookup(Table t, const uint64_t* __restrict__ keys, size_t n, int* __restrict__ slot_out,
-                         float* __restrict__ w_out, int* __restrict__ vrow_out, int2* __restrict__ wv_out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long key = keys[i];
-  int slot = -1;
-  if (key == kEmptyKey) {
-    raise(t.prog, DFB_ERR_INVALID);
-  } else {
-    uint64_t h = hash64(key) & t.mask;
-    for (uint64_t probe = 0; probe <= t.mask; ++probe) {
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.tab[h].key);
-      if (cur == key) { slot = (int)h; break; }
-      if (cur == kEmptyKey) {
-        if (!INSERT) break;
-        const unsigned long long prev = atomicCAS(&t.tab[h].key, kEmptyKey, key);
-        if (prev == kEmptyKey) {
-          const unsigned long long nk = atomicAdd(&t.state->n_keys, 1ULL) + 1;
-          atomicAdd(&t.prog->new_keys, 1ULL);
-          if (nk > t.max_keys) raise(t.prog, DFB_ERR_CAPACITY);
-          slot = (int)h;
-          break;
-        }
-        if (prev == key) { slot = (int)h; break; }
+__global__ void __launch_bounds__(256) k_lookup(Table t, const uint64_t* __restrict__ keys, size_t n_cap,
+                                                const unsigned long long* __restrict__ dn,
+                                                int* __restrict__ slot_out, float* __restrict__ w_out,
+                                                int* __restrict__ vrow_out, int2* __restrict__ wv_out) {
+  constexpr int ILP = 4;
+  const size_t n = dev_count(n_cap, dn);
+  const size_t tile = (size_t)blockDim.x * ILP;
+  for (size_t base = (size_t)blockIdx.x * tile; base < n; base += (size_t)gridDim.x * tile) {
+    unsigned long long key[ILP];
+    uint64_t h[ILP];
+    int4 lo[ILP];
+    float4 hi[ILP];
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
+      key[q] = i < n ? keys[i] : 0ULL;
+      h[q] = hash64(key[q]) & t.mask;
+    }
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
+      if (i < n) {
+        // L2-only loads: an entry inserted by another thread of this launch must not be served stale from L1
+        lo[q] = __ldcg(reinterpret_cast<const int4*>(&t.tab[h[q]]));
+        hi[q] = __ldcg(reinterpret_cast<const float4*>(&t.tab[h[q]].fea_cnt));
       }
-      h = (h + 1) & t.mask;
     }
-    if (INSERT && slot < 0) raise(t.prog, DFB_ERR_CAPACITY);
-  }
-  slot_out[i] = slot;
-  if (w_out) {
-    float w = 0.f;
-    int vr = -1;
-    if (slot >= 0) {
-      // second half of the entry {fea_cnt, w, sqrt_g, z}; first half holds vrow
-      w = t.tab[slot].w;
-      vr = t.tab[slot].vrow;
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
+      if (i >= n) continue;
+      int slot = -1, vr = -1;
+      float w = 0.f;
+      if (key[q] == kEmptyKey) {
+        raise(t.prog, DFB_ERR_INVALID);
+      } else {
+        const unsigned long long cur = ((unsigned long long)(unsigned)lo[q].y << 32) | (unsigned long long)(unsigned)lo[q].x;
+        if (cur == key[q]) {
+          slot = (int)h[q]; w = hi[q].y; vr = lo[q].z;
+        } else {
+          slot = table_find<INSERT>(t, key[q], h[q]);
+          if (slot >= 0 && w_out) { w = t.tab[slot].w; vr = t.tab[slot].vrow; }
+        }
+      }
+      slot_out[i] = slot;
+      if (w_out) {
+        w_out[i] = w;
+        vrow_out[i] = vr;
+        if (wv_out) wv_out[i] = make_int2(__float_as_int(w), vr);
+      }
     }
-    w_out[i] = w;
-    vrow_out[i] = vr;
-    if (wv_out) wv_out[i] = make_int2(__float_as_int(w), vr);
   }
 }
 
 // SGDUpdater::Update(kFeaCount), sgd_updater.cc:62-73
-__global__ void k_feacnt(Table t, Params p, const int* __restrict__ slot, size_t n,
-                         const float* __restrict__ cnt, int* __restrict__ flags) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int s = slot[i];
-  int f = 0;
-  if (s >= 0) {
-    Entry* e = &t.tab[s];
-    const float fc = __fadd_rn(e->fea_cnt, cnt[i]);
-    e->fea_cnt = fc;
-    if (p.V_dim > 0 && e->vrow < 0 && e->w != 0.f && fc > (float)p.V_threshold) f = 1;
+__global__ void k_feacnt(Table t, Params p, const int* __restrict__ slot, size_t n_cap,
+                         const unsigned long long* __restrict__ dn, const float* __restrict__ cnt,
+                         const int* __restrict__ cnt_cols, int* __restrict__ flags) {
+  const size_t n = dev_count(n_cap, dn);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = slot[i];
+    int f = 0;
+    if (s >= 0) {
+      Entry* e = &t.tab[s];
+      // counts either given, or the column lengths of the batch's CSC view (idx_frq, localizer.cc:41-46)
+      const float c = cnt ? cnt[i] : (float)(cnt_cols[i + 1] - cnt_cols[i]);
+      const float fc = __fadd_rn(e->fea_cnt, c);
+      e->fea_cnt = fc;
+      if (p.V_dim > 0 && e->vrow < 0 && e->w != 0.f && fc > (float)p.V_threshold) f = 1;
+    }
+    flags[i] = f;
   }
-  flags[i] = f;
 }
 
 // ---- glibc rand_r restated: next = next*1103515245 + 12345 three times per draw ----
@@ -142,32 +147,93 @@ __device__ __forceinline__ int rand_r_dev(unsigned* seed) {
   return (int)result;
 }
 
-// InitV (sgd_updater.cc:140-147) for the flagged keys; pos = exclusive scan of flags.
+// ---- ranks of the flagged keys without a host-known count: counts per tile of 32 keys, one-CTA
+// exclusive scan over the tiles, rank inside the tile from a ballot.  ws[0..1] = total (u64), ws[2+t] = tile t ----
+__global__ void k_flag_tiles(const int* __restrict__ flags, size_t n_cap, const unsigned long long* __restrict__ dn,
+                             int* __restrict__ ws) {
+  const size_t n = dev_count(n_cap, dn);
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t ntiles = (n + 31) / 32;
+  for (size_t tl = warp0; tl < ntiles; tl += nwarps) {
+    const size_t i = tl * 32 + lane;
+    const unsigned m = __ballot_sync(kFull, i < n && flags[i] != 0);
+    if (lane == 0) ws[2 + tl] = __popc(m);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_tile_scan(int* __restrict__ ws, size_t n_cap,
+                                                    const unsigned long long* __restrict__ dn) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const size_t n = dev_count(n_cap, dn);
+  const size_t ntiles = (n + 31) / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (size_t b0 = 0; b0 < ntiles; b0 += blockDim.x) {
+    const size_t i = b0 + threadIdx.x;
+    const int v = i < ntiles ? ws[2 + i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int wv = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFull, wv, o);
+        if (lane >= o) wv += y;
+      }
+      s_warp[lane] = wv;     // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + (wid ? s_warp[wid - 1] : 0) + (x - v);
+    if (i < ntiles) ws[2 + i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(ws) = (unsigned long long)s_carry;
+}
+
+// InitV (sgd_updater.cc:140-147) for the flagged keys, in ascending key order of the random stream.
 // A warp scans 32 flags at a time (almost always all zero) and cooperates on each set one.
-__global__ void k_initv(Table t, Params p, const int* __restrict__ slot, size_t n,
-                        const int* __restrict__ flags, const int* __restrict__ pos) {
+__global__ void k_initv(Table t, Params p, const int* __restrict__ slot, size_t n_cap,
+                        const unsigned long long* __restrict__ dn, const int* __restrict__ flags,
+                        const int* __restrict__ ws) {
+  const size_t n = dev_count(n_cap, dn);
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   const int k = p.V_dim;
   for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
     const size_t mine = base + lane;
-    unsigned m = __ballot_sync(kFull, mine < n && flags[mine] != 0);
-    if (m == 0) continue;
+    const unsigned m0 = __ballot_sync(kFull, mine < n && flags[mine] != 0);
+    if (m0 == 0) continue;
+    unsigned m = m0;
     const unsigned long long vbase = t.state->n_vrows;
     const unsigned seed0 = t.state->seed;
+    const unsigned long long tile_first = (unsigned long long)ws[2 + (base >> 5)];
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
       const size_t i = base + b;
-      const unsigned long long r = vbase + (unsigned long long)pos[i];
+      const unsigned long long rank = tile_first + (unsigned long long)__popc(m0 & ((1u << b) - 1u));
+      const unsigned long long r = vbase + rank;
       if (r >= t.vcap) { if (lane == 0) raise(t.prog, DFB_ERR_CAPACITY); continue; }
       float* Vr = t.V + r * t.rs;
       float* Cr = t.Vcg + r * t.rs;
       for (int l = lane; l < t.ks; l += 32) {
         float val = 0.f;
         if (l < k) {
-          unsigned sd = lcg_jump(seed0, 3ULL * ((unsigned long long)pos[i] * k + l));
+          unsigned sd = lcg_jump(seed0, 3ULL * (rank * k + l));
           const int rr = rand_r_dev(&sd);
           // (rand_r / (real_t)RAND_MAX - 0.5) * V_init_scale: float division, then double
           const float u01 = __fdiv_rn((float)rr, 2147483648.0f);
@@ -181,44 +247,13 @@ __global__ void k_initv(Table t, Params p, const int* __restrict__ slot, size_t 
   }
 }
 
-__global__ void k_initv_finalize(Table t, Params p, size_t n, const int* flags, const int* pos) {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || n == 0) return;
-  const unsigned long long total = (unsigned long long)pos[n - 1] + (unsigned long long)flags[n - 1];
+__global__ void k_initv_finalize(Table t, Params p, const int* ws) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long total = *reinterpret_cast<const unsigned long long*>(ws);
   if (total == 0) return;
   t.state->n_vrows += total;
   t.state->seed = lcg_jump(t.state->seed, 3ULL * total * (unsigned long long)p.V_dim);
   t.prog->new_vrows += total;
-}
-
-// ---- FTRL-proximal on w: SGDUpdater::UpdateW, sgd_updater.cc:104-127 ----
-// returns true when w went 0 -> nonzero (the InitV trigger :121-126)
-__device__ __forceinline__ bool ftrl_step(const Params& p, float gw, float& w, float& sqrt_g, float& z) {
-  const float sg = sqrt_g, w0 = w;
-  gw = __fadd_rn(gw, __fmul_rn(w0, p.l2));
-  sqrt_g = __fsqrt_rn(__fadd_rn(__fmul_rn(sg, sg), __fmul_rn(gw, gw)));
-  // z -= gw - (sqrt_g' - sg) / lr * w
-  z = __fsub_rn(z, __fsub_rn(gw, __fmul_rn(__fdiv_rn(__fsub_rn(sqrt_g, sg), p.lr), w0)));
-  const float l1 = p.l1;
-  if (z <= l1 && z >= -l1) {
-    w = 0.f;
-  } else {
-    const float eta = __fdiv_rn(__fadd_rn(p.lr_beta, sqrt_g), p.lr);
-    w = __fdiv_rn(z > 0.f ? __fsub_rn(z, l1) : __fadd_rn(z, l1), eta);
-  }
-  return w0 == 0.f && w != 0.f;
-}
-
-// ---- AdaGrad on one V component: SGDUpdater::UpdateV, sgd_updater.cc:129-138 ----
-__device__ __forceinline__ void adagrad_step(const Params& p, float gV, float& v, float& cg) {
-  const float g = __fadd_rn(gV, __fmul_rn(p.V_l2, v));
-  cg = __fsqrt_rn(__fadd_rn(__fmul_rn(cg, cg), __fmul_rn(g, g)));
-  const float eta = __fdiv_rn(p.V_lr, __fadd_rn(cg, p.V_lr_beta));
-  v = __fsub_rn(v, __fmul_rn(eta, g));
-}
-
-// penalty of one w (sgd_learner.cc:257 ; evaluated in fp32 here, double there)
-__device__ __forceinline__ float pen_w(const Params& p, float w) {
-  return p.l1 * fabsf(w) + 0.5f * p.l2 * w * w;
 }
 
 // fused scatter-finalize + FTRL + AdaGrad over dense per-key gradient rows.
@@ -364,7 +399,9 @@ __global__ void __launch_bounds__(256) k_update_ragged(Table t, Params p, const 
 // V + i*ks when dense (a pulled [n][ks] buffer with vrow[i] >= 0 meaning "present").
 __global__ void __launch_bounds__(256) k_penalty(Params p, DevProgress* prog, const float* __restrict__ w_arr,
                                                  const int* __restrict__ vrow, const float* __restrict__ V,
-                                                 int ks, int dense, size_t n) {
+                                                 int ks, int dense, size_t n_cap,
+                                                 const unsigned long long* __restrict__ dn) {
+  const size_t n = dev_count(n_cap, dn);
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -383,16 +420,18 @@ __global__ void __launch_bounds__(256) k_penalty(Params p, DevProgress* prog, co
 }
 
 // w and vrow of already-located entries (the Pull of the fused path after a feature-count push)
-__global__ void k_pull_view(Table t, const int* __restrict__ slot, size_t n, float* __restrict__ w_out,
+__global__ void k_pull_view(Table t, const int* __restrict__ slot, size_t n_cap,
+                            const unsigned long long* __restrict__ dn, float* __restrict__ w_out,
                             int* __restrict__ vrow_out, int2* __restrict__ wv_out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int s = slot[i];
-  const float w = s >= 0 ? t.tab[s].w : 0.f;
-  const int vr = s >= 0 ? t.tab[s].vrow : -1;
-  w_out[i] = w;
-  vrow_out[i] = vr;
-  if (wv_out) wv_out[i] = make_int2(__float_as_int(w), vr);
+  const size_t n = dev_count(n_cap, dn);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = slot[i];
+    const float w = s >= 0 ? t.tab[s].w : 0.f;
+    const int vr = s >= 0 ? t.tab[s].vrow : -1;
+    w_out[i] = w;
+    vrow_out[i] = vr;
+    if (wv_out) wv_out[i] = make_int2(__float_as_int(w), vr);
+  }
 }
 
 // SGDUpdater::Get: lens (sgd_updater.cc:46-53)
@@ -612,7 +651,8 @@ __device__ __forceinline__ void load_occ(const void* occ, int o, uint32_t& row, 
 #endif
 template <int K, bool HAS_VAL, bool APPLY, int SRC = 0>
 __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, Params p, const int* __restrict__ slot,
-                                                    const int* __restrict__ pull_vrow, size_t n,
+                                                    const int* __restrict__ pull_vrow, size_t n_cap,
+                                                    const unsigned long long* __restrict__ dn,
                                                     const int* __restrict__ col_start,
                                                     const int* __restrict__ col_end,
                                                     const void* __restrict__ occ,
@@ -620,31 +660,35 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
                                                     const float* __restrict__ pxv, int* __restrict__ flags,
                                                     int acc_pen, float* __restrict__ gw_out,
                                                     const float* __restrict__ V_pulled,
-                                                    float* __restrict__ gV_out, SegDst seg) {
+                                                    float* __restrict__ gV_out, SegDst seg, ShardApply sa) {
+  const unsigned n = (unsigned)dev_count(n_cap, dn);     // < 2^31 (checked by the host): 32-bit index math
   constexpr int LPR = K / 4;
   constexpr int G = 32 / LPR;
   constexpr int NPASS = 32 / G;
   constexpr int UNRB = NPASS >= DFB_BU_UNRB ? DFB_BU_UNRB : 1;
   constexpr int kHeavy = 64;     // occurrence-list length above which a key is reduced cooperatively
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
   float pen = 0.f;
-  const size_t npad = (n + 31) / 32 * 32;
-  for (size_t b0 = warp0 * 32; b0 < n; b0 += nwarps * 32) {
+  const unsigned npad = (n + 31u) / 32u * 32u;
+  for (unsigned b0 = warp0 * 32u; b0 < n; b0 += nwarps * 32u) {
     // start at this rank's own key segment and go round: at any moment the ranks of a sharded
     // step store into different peers (seg.rot == 0 outside the peer-store path)
-    size_t base = b0 + (size_t)seg.rot;
+    unsigned base = b0 + (unsigned)seg.rot;
     if (base >= npad) base -= npad;
     // ---------------- phase A: one key per lane ----------------
-    const size_t i = base + lane;
+    const unsigned i = base + lane;
     const bool active = i < n;
     int s = -1, vr = -1, o0 = 0, o1 = 0;
     if (active) {
       vr = pull_vrow[i];
-      if (SRC == 0) { o0 = col_start[i]; o1 = col_end[i]; }
+      if (SRC != 1) { o0 = col_start[i]; o1 = col_end[i]; }
       if (APPLY) s = slot[i];
     }
+    // SRC 2 (owner side of the fused sharded store): this key was already updated in this step by a
+    // lower-rank worker's push, so the pull-time V row is the saved copy, not the table row
+    const int cf = (SRC == 2 && active && sa.conf != nullptr) ? (int)sa.conf[i] : 0;
     Entry* e = nullptr;
     float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (APPLY && s >= 0) {
@@ -676,7 +720,7 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
         }
       }
     }
-    if (SRC == 0) {
+    if (SRC != 1) {
       unsigned hm = __ballot_sync(kFull, heavy);
       while (hm) {
         const int hl = __ffs(hm) - 1;
@@ -700,7 +744,7 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
     if (APPLY) {
       if (s >= 0) {
         if (vr >= 0) vr = SRC == 1 ? e->vrow : vr;   // SRC 1: pull_vrow is the worker's has_V flag
-        if (acc_pen) pen += pen_w(p, sc.y);
+        if (acc_pen) pen += pen_w(p, SRC == 2 ? sa.w_pulled[i] : sc.y);   // penalty of the PULLED weights (sgd_learner.cc:148)
         const bool became_nz = ftrl_step(p, gw, sc.y, sc.z, sc.w);
         *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
         flags[i] = (became_nz && p.V_dim > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
@@ -714,7 +758,7 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
       } else {   // the owner's receive buffer (peer memory over NVLink)
         int sg = 0;
         while (sg + 1 < seg.nseg && (int)i >= seg.bounds[sg + 1]) ++sg;
-        seg.gw[sg][i - (size_t)seg.bounds[sg]] = gw;
+        seg.gw[sg][i - (unsigned)seg.bounds[sg]] = gw;
       }
       if (acc_pen) pen += pen_w(p, slot ? __int_as_float(slot[i]) : 0.f);   // worker: slot aliases the pulled w
     }
@@ -722,7 +766,7 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; pass += UNRB) {
       float4 v[UNRB], c[UNRB], g[UNRB];
-      int vrk[UNRB], o0k[UNRB], o1k[UNRB];
+      int vrk[UNRB], o0k[UNRB], o1k[UNRB], cfk[UNRB];
       float xxpk[UNRB];
 #pragma unroll
       for (int q = 0; q < UNRB; ++q) {
@@ -731,6 +775,7 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
         o0k[q] = __shfl_sync(kFull, o0, kk);
         o1k[q] = __shfl_sync(kFull, o1, kk);
         xxpk[q] = __shfl_sync(kFull, xxp, kk);
+        cfk[q] = SRC == 2 ? __shfl_sync(kFull, cf, kk) : 0;
         const uint32_t r0 = __shfl_sync(kFull, row0, kk);
         const float xx0 = __shfl_sync(kFull, x0, kk);
         v[q] = c[q] = g[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -742,11 +787,11 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
             c[q] = *reinterpret_cast<const float4*>(Vr + t.ks);
           } else {
             // the pulled row (dense [n][K] buffer): the worker applies "- V * XXp" itself (fm_loss.h:181-188)
-            const size_t ik = base + (size_t)((pass + q) * G + grp);
+            const size_t ik = base + (unsigned)((pass + q) * G + grp);
             v[q] = __ldg(reinterpret_cast<const float4*>(V_pulled + ik * (size_t)K + sub * 4));
           }
           if (SRC == 1) {
-            const size_t ik = base + (size_t)((pass + q) * G + grp);
+            const size_t ik = base + (unsigned)((pass + q) * G + grp);
             g[q] = __ldg(reinterpret_cast<const float4*>(pxv + ik * (size_t)K + sub * 4));   // pxv aliases gV_in
           } else if (o1k[q] > o0k[q]) {
             const float4 tt = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)r0 * K + sub * 4));
@@ -778,17 +823,22 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
           }
         }
         if (APPLY) {
-          if (acc_pen) pen += 0.5f * p.V_l2 * (v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w);
+          // the worker's gradient is taken at the PULLED V (fm_loss.h:181-188); it differs from the table row
+          // only for a key a lower-rank worker's push has already updated in this step (SRC 2)
+          float4 vp = v[q];
+          if (SRC == 2 && cfk[q])
+            vp = __ldg(reinterpret_cast<const float4*>(sa.vsave + (size_t)(base + (unsigned)((pass + q) * G + grp)) * (size_t)K + sub * 4));
+          if (acc_pen) pen += 0.5f * p.V_l2 * (vp.x * vp.x + vp.y * vp.y + vp.z * vp.z + vp.w * vp.w);
           const float xp = xxpk[q];
-          adagrad_step(p, __fsub_rn(g[q].x, __fmul_rn(v[q].x, xp)), v[q].x, c[q].x);
-          adagrad_step(p, __fsub_rn(g[q].y, __fmul_rn(v[q].y, xp)), v[q].y, c[q].y);
-          adagrad_step(p, __fsub_rn(g[q].z, __fmul_rn(v[q].z, xp)), v[q].z, c[q].z);
-          adagrad_step(p, __fsub_rn(g[q].w, __fmul_rn(v[q].w, xp)), v[q].w, c[q].w);
+          adagrad_step(p, __fsub_rn(g[q].x, __fmul_rn(vp.x, xp)), v[q].x, c[q].x);
+          adagrad_step(p, __fsub_rn(g[q].y, __fmul_rn(vp.y, xp)), v[q].y, c[q].y);
+          adagrad_step(p, __fsub_rn(g[q].z, __fmul_rn(vp.z, xp)), v[q].z, c[q].z);
+          adagrad_step(p, __fsub_rn(g[q].w, __fmul_rn(vp.w, xp)), v[q].w, c[q].w);
           float* Vr = t.V + (size_t)vrk[q] * t.rs + sub * 4;
           *reinterpret_cast<float4*>(Vr) = v[q];
           *reinterpret_cast<float4*>(Vr + t.ks) = c[q];
         } else {
-          const size_t ik = base + (size_t)((pass + q) * G + grp);
+          const size_t ik = base + (unsigned)((pass + q) * G + grp);
           const float xp = xxpk[q];
           if (acc_pen) pen += 0.5f * p.V_l2 * (v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w);
           float* grow = gV_out + ik * (size_t)K;
@@ -804,7 +854,7 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
       }
     }
     // ---------------- hot keys: the whole warp reduces one occurrence list ----------------
-    if (SRC == 0) {
+    if (SRC != 1) {
       unsigned hm = __ballot_sync(kFull, active && (o1 - o0) > kHeavy && vr >= 0);
       while (hm) {
         const int hl = __ffs(hm) - 1;
@@ -812,7 +862,8 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
         const int hvr = __shfl_sync(kFull, vr, hl);
         const int ho0 = __shfl_sync(kFull, o0, hl), ho1 = __shfl_sync(kFull, o1, hl);
         const float hxp = __shfl_sync(kFull, xxp, hl);
-        const size_t ik = base + (size_t)hl;
+        const int hcf = SRC == 2 ? __shfl_sync(kFull, cf, hl) : 0;
+        const size_t ik = base + (unsigned)hl;
         float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), hc = hv;
         float* Vr = nullptr;
         if (grp == 0) {
@@ -852,12 +903,15 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
           hg.z += __shfl_xor_sync(kFull, hg.z, o); hg.w += __shfl_xor_sync(kFull, hg.w, o);
         }
         if (grp == 0) {
-          if (acc_pen) pen += 0.5f * p.V_l2 * (hv.x * hv.x + hv.y * hv.y + hv.z * hv.z + hv.w * hv.w);
+          float4 hp = hv;      // the pulled row (see phase B)
+          if (SRC == 2 && hcf)
+            hp = __ldg(reinterpret_cast<const float4*>(sa.vsave + ik * (size_t)K + sub * 4));
+          if (acc_pen) pen += 0.5f * p.V_l2 * (hp.x * hp.x + hp.y * hp.y + hp.z * hp.z + hp.w * hp.w);
           if (APPLY) {
-            adagrad_step(p, __fsub_rn(hg.x, __fmul_rn(hv.x, hxp)), hv.x, hc.x);
-            adagrad_step(p, __fsub_rn(hg.y, __fmul_rn(hv.y, hxp)), hv.y, hc.y);
-            adagrad_step(p, __fsub_rn(hg.z, __fmul_rn(hv.z, hxp)), hv.z, hc.z);
-            adagrad_step(p, __fsub_rn(hg.w, __fmul_rn(hv.w, hxp)), hv.w, hc.w);
+            adagrad_step(p, __fsub_rn(hg.x, __fmul_rn(hp.x, hxp)), hv.x, hc.x);
+            adagrad_step(p, __fsub_rn(hg.y, __fmul_rn(hp.y, hxp)), hv.y, hc.y);
+            adagrad_step(p, __fsub_rn(hg.z, __fmul_rn(hp.z, hxp)), hv.z, hc.z);
+            adagrad_step(p, __fsub_rn(hg.w, __fmul_rn(hp.w, hxp)), hv.w, hc.w);
             *reinterpret_cast<float4*>(Vr) = hv;
             *reinterpret_cast<float4*>(Vr + t.ks) = hc;
           } else {
@@ -905,13 +959,12 @@ int launch_table_init(Table& t, unsigned seed, cudaStream_t s) {
   return 1;
 }
 
-int launch_lookup(Table& t, const uint64_t* keys, size_t n, bool insert, int* slot_out, float* w_out,
-                  int* vrow_out, int2* wv_out, cudaStream_t s) {
+int launch_lookup(Table& t, const uint64_t* keys, size_t n, const unsigned long long* dn, bool insert,
+                  int* slot_out, float* w_out, int* vrow_out, int2* wv_out, cudaStream_t s) {
   if (n == 0) return 0;
-  const int threads = 256;
-  const int grid = (int)((n + threads - 1) / threads);
-  if (insert) k_lookup<true><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out, wv_out);
-  else        k_lookup<false><<<grid, threads, 0, s>>>(t, keys, n, slot_out, w_out, vrow_out, wv_out);
+  const int grid = grid_for(n, 256 * 4, 148 * 8);
+  if (insert) k_lookup<true><<<grid, 256, 0, s>>>(t, keys, n, dn, slot_out, w_out, vrow_out, wv_out);
+  else        k_lookup<false><<<grid, 256, 0, s>>>(t, keys, n, dn, slot_out, w_out, vrow_out, wv_out);
   return 1;
 }
 
@@ -928,20 +981,22 @@ size_t sort_tmp_bytes(size_t n) {
   return bytes;
 }
 
-int launch_initv(Table& t, const Params& p, const int* slot, size_t n, int* flags, int* pos, void* cub_tmp,
-                 size_t cub_bytes, cudaStream_t s) {
+int launch_initv(Table& t, const Params& p, const int* slot, size_t n, const unsigned long long* dn, int* flags,
+                 int* ws, cudaStream_t s) {
   if (n == 0 || p.V_dim == 0) return 0;
-  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, (int)n, s);
-  k_initv<<<grid_warps((n + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, p, slot, n, flags, pos);
-  k_initv_finalize<<<1, 32, 0, s>>>(t, p, n, flags, pos);
-  return 4;  // the CUB scan is 2 kernels
+  const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);
+  k_flag_tiles<<<grid, 256, 0, s>>>(flags, n, dn, ws);
+  k_tile_scan<<<1, 1024, 0, s>>>(ws, n, dn);
+  k_initv<<<grid, 256, 0, s>>>(t, p, slot, n, dn, flags, ws);
+  k_initv_finalize<<<1, 32, 0, s>>>(t, p, ws);
+  return 4;
 }
 
-int launch_feacnt(Table& t, const Params& p, const int* slot, size_t n, const float* cnt, int* flags,
-                  int* pos, void* cub_tmp, size_t cub_bytes, cudaStream_t s) {
+int launch_feacnt(Table& t, const Params& p, const int* slot, size_t n, const unsigned long long* dn,
+                  const float* cnt, const int* cnt_cols, int* flags, int* ws, cudaStream_t s) {
   if (n == 0) return 0;
-  k_feacnt<<<(int)((n + 255) / 256), 256, 0, s>>>(t, p, slot, n, cnt, flags);
-  return 1 + launch_initv(t, p, slot, n, flags, pos, cub_tmp, cub_bytes, s);
+  k_feacnt<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(t, p, slot, n, dn, cnt, cnt_cols, flags);
+  return 1 + launch_initv(t, p, slot, n, dn, flags, ws, s);
 }
 
 int launch_lens_scan(const int* lens, size_t n, int* pos, void* cub_tmp, size_t cub_bytes, cudaStream_t s) {
@@ -996,16 +1051,16 @@ int launch_update_ragged(Table& t, const Params& p, const int* slot, size_t n, c
 }
 
 int launch_penalty(const Params& p, DevProgress* prog, const float* w_arr, const int* vrow, const float* V,
-                   int ks, int dense, size_t n, cudaStream_t s) {
+                   int ks, int dense, size_t n, const unsigned long long* dn, cudaStream_t s) {
   if (n == 0) return 0;
-  k_penalty<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(p, prog, w_arr, vrow, V, ks, dense, n);
+  k_penalty<<<grid_warps(n, 8, 148 * 8), 256, 0, s>>>(p, prog, w_arr, vrow, V, ks, dense, n, dn);
   return 1;
 }
 
-int launch_pull_view(Table& t, const int* slot, size_t n, float* w_out, int* vrow_out, int2* wv_out,
-                     cudaStream_t s) {
+int launch_pull_view(Table& t, const int* slot, size_t n, const unsigned long long* dn, float* w_out,
+                     int* vrow_out, int2* wv_out, cudaStream_t s) {
   if (n == 0) return 0;
-  k_pull_view<<<(int)((n + 255) / 256), 256, 0, s>>>(t, slot, n, w_out, vrow_out, wv_out);
+  k_pull_view<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(t, slot, n, dn, w_out, vrow_out, wv_out);
   return 1;
 }
 
@@ -1058,18 +1113,23 @@ int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t 
 }
 
 int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,
-                      const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
-                      const float* p_row, const float* pxv, int* flags, int acc_pen, cudaStream_t s) {
+                      const unsigned long long* dn, const int* col_start, const int* col_end,
+                      const void* occ_sorted, bool valued, const float* p_row, const float* pxv, int* flags,
+                      int acc_pen, const ShardApply* shard, cudaStream_t s) {
   if (n == 0) return 0;
   SegDst noseg;
   memset(&noseg, 0, sizeof(noseg));
+  ShardApply sa;
+  memset(&sa, 0, sizeof(sa));
+  if (shard) sa = *shard;
+#define DFB_BU_(K, VAL, SRC)                                                                                   \
+  k_bwd_update<K, VAL, true, SRC><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, dn, col_start, col_end, occ_sorted, \
+                                                       p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg, sa)
 #define DFB_BU(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
-    if (valued) k_bwd_update<K, true, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end, \
-                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg);               \
-    else k_bwd_update<K, false, true><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, col_start, col_end,     \
-                   occ_sorted, p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg);               \
+    if (shard) { if (valued) DFB_BU_(K, true, 2); else DFB_BU_(K, false, 2); }                             \
+    else       { if (valued) DFB_BU_(K, true, 0); else DFB_BU_(K, false, 0); }                             \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_BU(8); return 1;
@@ -1079,6 +1139,7 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
     case 128: DFB_BU(128); return 1;
   }
 #undef DFB_BU
+#undef DFB_BU_
   return -1;
 }
 
@@ -1093,13 +1154,15 @@ int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_
   SegDst sd;
   if (seg) sd = *seg; else memset(&sd, 0, sizeof(sd));
   const int* w_alias = reinterpret_cast<const int*>(w_pulled);
+  ShardApply nosa;
+  memset(&nosa, 0, sizeof(nosa));
 #define DFB_BD(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
-    if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, col_start, col_end, \
-                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd);                 \
-    else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, col_start, col_end,      \
-                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd);                 \
+    if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, nullptr, col_start, col_end, \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd, nosa);           \
+    else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, nullptr, col_start, col_end, \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd, nosa);           \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_BD(8); return 1;
@@ -1119,11 +1182,13 @@ int launch_update_pushed(Table& t, const Params& p, const int* slot, const int* 
   if (n == 0) return 0;
   SegDst noseg;
   memset(&noseg, 0, sizeof(noseg));
+  ShardApply nosa;
+  memset(&nosa, 0, sizeof(nosa));
 #define DFB_UP(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
-    k_bwd_update<K, false, true, 1><<<grid, 256, 0, s>>>(t, p, slot, hasv, n, nullptr, nullptr, nullptr, gw, \
-                                                          gV, flags, 0, nullptr, nullptr, nullptr, noseg);  \
+    k_bwd_update<K, false, true, 1><<<grid, 256, 0, s>>>(t, p, slot, hasv, n, nullptr, nullptr, nullptr, nullptr, gw, \
+                                                          gV, flags, 0, nullptr, nullptr, nullptr, noseg, nosa); \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_UP(8); return 1;

@@ -1,0 +1,401 @@
+// difacto_b200/csrc/shard.cu -- host side of the NVLink-sharded model store (dfb_shard_* of the C-ABI).
+//
+// Replaces, for the FM-SGD hot path, the worker/server exchange the reference was written for
+// (src/sgd/sgd_learner.cc:78-89 + Store::Push/Pull over ps-lite KVWorker/KVServer,
+// ps-lite/include/ps/kv_app.h:406-460; difacto's own distributed Store is LOG(FATAL) "not implemented",
+// src/store/store.cc:9-11).  One engine per GPU is at the same time a WORKER (its own minibatch) and the
+// OWNER of one contiguous range of the reversed key space (postoffice.cc:127-136).  See kernels_shard.cu
+// for what crosses NVLink.  One step of every rank, all asynchronous, no host synchronisation:
+//
+//   stream W (worker)            stream O (owner = the engine's main stream)            stream F (finish)
+//   localize raw ids (GPU)
+//   segment bounds, scatter the
+//   CSC/CSR slices -> owners  --struct-->  lookup(+feacnt) of all workers' key segments
+//                                          partial interaction sums of all workers' rows
+//   add partials, pred/loss/p <--part----  (stored into the workers' mailboxes)
+//   p, p*XV -> owners         --pxv----->  per worker, rank order: per-key gradient from its
+//   AUC (aux stream)                       column lists + FTRL/AdaGrad in place, InitV     --done--> penalties,
+//                                                                                          Progress snapshot
+// W of step t+1 (localize, scatter) overlaps O of step t (update); mailbox slots are double-buffered by step
+// parity.  Dependencies on the SAME GPU are CUDA events, dependencies on other GPUs are step counters in
+// peer memory polled by one-warp kernels (with a timeout), so the FIFO order of the host's enqueues is
+// deadlock-free whatever the stream-to-hardware-queue mapping is.
+#include <cstring>
+
+#include "engine_internal.cuh"
+#include "shard_layout.cuh"
+
+using namespace dfb;  // NOLINT
+
+struct ShardState {
+  int rank = 0, S = 1;
+  ShardLayout lay;
+  size_t Bcap = 0, Ncap = 0;
+  void* mailbox = nullptr;
+  void* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool connected = false;
+  cudaStream_t w_stream = nullptr, f_stream = nullptr;
+  cudaEvent_t ev_struct[2] = {}, ev_part[2] = {}, ev_reduce[2] = {}, ev_auc[2] = {}, ev_upd[2] = {}, ev_fin[2] = {};
+  uint64_t step = 0;
+  dfb_engine::LocSet L;
+  DevBuf wb, rowcnt, pred[2];
+  DevBuf slot, w, vrow, wv, conf, vsave, flags, ws;
+  DevProgress* dprog = nullptr;   // device: [0,S) per-worker scratch, [S,S+2) worker Progress by parity, [S+2,S+4) staging
+  long long timeout_cycles = 0;
+  DevProgress* src_prog(int r) { return dprog + r; }
+  DevProgress* prog_w(int d) { return dprog + S + d; }
+  DevProgress* stage(int d) { return dprog + S + 2 + d; }
+};
+
+namespace {
+
+int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
+               const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready,
+               cudaEvent_t consumed) {
+  ShardState* shp = h->shard;
+  if (!shp) return h->fail(DFB_ERR_INVALID, "dfb_shard_init was not called");
+  ShardState& sh = *shp;
+  if (!sh.connected) return h->fail(DFB_ERR_INVALID, "dfb_shard_connect was not called");
+  if (nrows > sh.Bcap || nnz > sh.Ncap) return h->fail(DFB_ERR_CAPACITY, "batch larger than dfb_shard_init's max_rows / max_nnz");
+  if (is_train && !h->has_aux) return h->fail(DFB_ERR_INVALID, "no aux data");   // CHECK(has_aux_), sgd_updater.cc:75
+  if (nrows && !d_lab) return h->fail(DFB_ERR_INVALID, "label is NULL");
+  const ShardLayout& lay = sh.lay;
+  const int S = sh.S, me = sh.rank, K = h->prm.V_dim;
+  const uint64_t t = sh.step;
+  const int d = (int)(t & 1);
+  const unsigned long long fv = t + 1;
+  const bool valued = d_val != nullptr;
+  const unsigned remote = ((1u << S) - 1u) & ~(1u << me);
+  cudaStream_t W = sh.w_stream, O = h->stream, A = h->aux_stream, F = sh.f_stream;
+  void* mine = sh.mailbox;
+  const size_t Kseg = lay.Kseg;
+
+  // ------------------------------- W part 1: localize, slice, scatter -------------------------------
+  if (inputs_ready) DFB_CUDA(h, cudaStreamWaitEvent(W, inputs_ready, 0));
+  if (t >= 2) DFB_CUDA(h, cudaStreamWaitEvent(W, sh.ev_fin[d], 0));     // parity slots of step t-2 are free again
+  size_t Ucap = 0;
+  DFB_TRY(dfbh::localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, sh.L, W, false, false, &Ucap));   // Localizer(-1), sgd_learner.cc:203
+  DFB_TRY(h->ensure(sh.rowcnt, (size_t)S * (nrows + 1) * sizeof(int)));
+  DFB_TRY(h->ensure(sh.pred[d], (nrows ? nrows : 1) * sizeof(float)));
+  ShardBounds* wb = sh.wb.as<ShardBounds>();
+  h->launches += launch_shard_bounds(sh.L.keys.as<uint64_t>(), sh.L.dU(), Ucap, sh.L.col_start.as<int>(), nnz, S, Kseg,
+                                     lay.Nseg, wb, h->tab.prog, W);
+  {
+    ScatterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.S = S; a.me = me; a.wb = wb; a.keys = sh.L.keys.as<uint64_t>(); a.col_start = sh.L.col_start.as<int>();
+    a.occ = sh.L.occ_sorted.p; a.nrows = nrows;
+    a.flags = (is_train ? 1ULL : 0ULL) | (push_cnt ? 2ULL : 0ULL) | (valued ? 4ULL : 0ULL);
+    a.step = fv;
+    RowptrDst rd;
+    FillDst fd;
+    memset(&rd, 0, sizeof(rd));
+    memset(&fd, 0, sizeof(fd));
+    for (int s = 0; s < S; ++s) {
+      a.hdr_dst[s] = lay.at<ShardHdr>(sh.peer[s], lay.off_hdr, lay.str_hdr, d, me);
+      a.keys_dst[s] = lay.at<uint64_t>(sh.peer[s], lay.off_keys, lay.str_keys, d, me);
+      a.cstart_dst[s] = lay.at<int>(sh.peer[s], lay.off_cstart, lay.str_cstart, d, me);
+      a.occ_dst[s] = lay.at<void>(sh.peer[s], lay.off_occ, lay.str_occ, d, me);
+      rd.rowptr_dst[s] = lay.at<uint64_t>(sh.peer[s], lay.off_rowptr, lay.str_rowptr, d, me);
+      fd.ridx_dst[s] = lay.at<uint32_t>(sh.peer[s], lay.off_ridx, lay.str_ridx, d, me);
+      fd.rval_dst[s] = lay.at<float>(sh.peer[s], lay.off_rval, lay.str_rval, d, me);
+    }
+    h->launches += launch_shard_scatter(a, valued, nnz ? nnz : 1, W);
+    h->launches += launch_shard_subcsr(d_off, sh.L.lidx.as<uint32_t>(), d_val, nrows, wb, S, sh.rowcnt.as<int>(), rd, fd, W);
+  }
+  {
+    SignalDst sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.n = S;
+    for (int s = 0; s < S; ++s) sd.flag[s] = s == me ? nullptr : lay.flag(sh.peer[s], ShardLayout::F_STRUCT, me);
+    if (remote) h->launches += launch_shard_signal(sd, fv, W);
+  }
+  DFB_CUDA(h, cudaEventRecord(sh.ev_struct[d], W));
+
+  // ------------------------------- O part 1: lookup, partial interaction sums -------------------------------
+  DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_struct[d], 0));
+  h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_STRUCT, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, O);
+  LookupArgs la;
+  memset(&la, 0, sizeof(la));
+  la.S = S; la.Kseg = Kseg;
+  la.stamp = (is_train && S > 1) ? (unsigned)((fv & 0xFFFFFFULL) ? (fv & 0xFFFFFFULL) : 1ULL) : 0u;
+  la.slot = sh.slot.as<int>(); la.w = sh.w.as<float>(); la.vrow = sh.vrow.as<int>(); la.wv = sh.wv.as<int2>();
+  const ShardHdr* hdr[8];
+  for (int r = 0; r < S; ++r) {
+    hdr[r] = lay.at<ShardHdr>(mine, lay.off_hdr, lay.str_hdr, d, r);
+    la.hdr[r] = hdr[r];
+    la.keys[r] = lay.at<uint64_t>(mine, lay.off_keys, lay.str_keys, d, r);
+  }
+  // a validation / prediction batch must not grow the table (a missing entry reads as w = 0, no V)
+  h->launches += launch_shard_lookup(h->tab, la, is_train || push_cnt, O);
+  int* flags = sh.flags.as<int>();
+  int* ws = sh.ws.as<int>();
+  if (push_cnt) {
+    // Push(kFeaCount) before Pull (sgd_learner.cc:214-217): one Update per worker, rank order
+    for (int r = 0; r < S; ++r)
+      h->launches += launch_feacnt(h->tab, h->prm, la.slot + (size_t)r * Kseg, Kseg, &hdr[r]->nkeys, nullptr,
+                                   lay.at<int>(mine, lay.off_cstart, lay.str_cstart, d, r), flags, ws, O);
+    for (int r = 0; r < S; ++r)
+      h->launches += launch_pull_view(h->tab, la.slot + (size_t)r * Kseg, Kseg, &hdr[r]->nkeys, la.w + (size_t)r * Kseg,
+                                      la.vrow + (size_t)r * Kseg, la.wv + (size_t)r * Kseg, O);
+  }
+  if (la.stamp) h->launches += launch_shard_conflicts(h->tab, la, sh.conf.as<unsigned char>(), sh.vsave.as<float>(), K, O);
+  {
+    PartArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.nsrc = S; pa.rot = me; pa.bcap = sh.Bcap;
+    for (int r = 0; r < S; ++r) {
+      pa.s[r].rowptr = lay.at<uint64_t>(mine, lay.off_rowptr, lay.str_rowptr, d, r);
+      pa.s[r].ridx = lay.at<uint32_t>(mine, lay.off_ridx, lay.str_ridx, d, r);
+      pa.s[r].rval = valued ? lay.at<float>(mine, lay.off_rval, lay.str_rval, d, r) : nullptr;
+      pa.s[r].wv = la.wv + (size_t)r * Kseg;
+      pa.s[r].hdr = hdr[r];
+      pa.s[r].out_xv = lay.at<float>(sh.peer[r], lay.off_part_xv, lay.str_part_xv, d, me);
+      pa.s[r].out_sc = lay.at<float2>(sh.peer[r], lay.off_part_sc, lay.str_part_sc, d, me);
+    }
+    FmView v;
+    memset(&v, 0, sizeof(v));
+    v.vbase = h->tab.V; v.vstride = h->tab.rs; v.l2hint = h->l2_hints;
+    int nl = launch_fm_partial(K, valued, v, pa, O);
+    if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
+    h->launches += nl;
+  }
+  {
+    SignalDst sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.n = S;
+    for (int r = 0; r < S; ++r) sd.flag[r] = r == me ? nullptr : lay.flag(sh.peer[r], ShardLayout::F_PART, me);
+    if (remote) h->launches += launch_shard_signal(sd, fv, O);
+  }
+  DFB_CUDA(h, cudaEventRecord(sh.ev_part[d], O));
+
+  // ------------------------------- W part 2: reduce the partials, p and p*XV back -------------------------------
+  DFB_CUDA(h, cudaStreamWaitEvent(W, sh.ev_part[d], 0));
+  h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_PART, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, W);
+  {
+    ReduceArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.S = S; ra.me = me; ra.train = is_train ? 1 : 0; ra.nrows = nrows;
+    for (int s = 0; s < S; ++s) {
+      ra.part_xv[s] = lay.at<float>(mine, lay.off_part_xv, lay.str_part_xv, d, s);
+      ra.part_sc[s] = lay.at<float2>(mine, lay.off_part_sc, lay.str_part_sc, d, s);
+      ra.p_dst[s] = lay.at<float>(sh.peer[s], lay.off_p, lay.str_p, d, me);
+      ra.pxv_dst[s] = lay.at<float>(sh.peer[s], lay.off_pxv, lay.str_pxv, d, me);
+    }
+    ra.label = d_lab; ra.pred = sh.pred[d].as<float>(); ra.prog = sh.prog_w(d);
+    int nl = launch_shard_reduce(K, ra, W);
+    if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
+    h->launches += nl;
+  }
+  {
+    SignalDst sd;
+    memset(&sd, 0, sizeof(sd));
+    sd.n = S;
+    for (int s = 0; s < S; ++s) sd.flag[s] = s == me ? nullptr : lay.flag(sh.peer[s], ShardLayout::F_PXV, me);
+    if (remote) h->launches += launch_shard_signal(sd, fv, W);
+  }
+  DFB_CUDA(h, cudaEventRecord(sh.ev_reduce[d], W));
+  const bool auc = h->compute_auc && nrows;
+  if (auc) {
+    DFB_TRY(h->ensure(h->auc_k, nrows * sizeof(float)));
+    DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
+    DFB_TRY(h->ensure(h->auc_tmp, sort_tmp_bytes(nrows)));
+    DFB_CUDA(h, cudaStreamWaitEvent(A, sh.ev_reduce[d], 0));
+    h->launches += launch_auc(d_lab, sh.pred[d].as<float>(), nrows, h->auc_k.as<float>(), h->auc_v.as<float>(),
+                              h->auc_tmp.p, h->auc_tmp.bytes, &sh.prog_w(d)->auc, A);
+    DFB_CUDA(h, cudaEventRecord(sh.ev_auc[d], A));
+  }
+
+  // ------------------------------- O part 2: one Update per worker, rank order -------------------------------
+  for (int r = 0; r < S; ++r) {
+    if (r == me) DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_reduce[d], 0));
+    else h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_PXV, r), 8, 1u, fv, sh.timeout_cycles, h->tab.prog, O);
+    const size_t o = (size_t)r * Kseg;
+    const int* cstart = lay.at<int>(mine, lay.off_cstart, lay.str_cstart, d, r);
+    if (is_train) {
+      Table tt = h->tab;
+      tt.prog = sh.src_prog(r);
+      ShardApply ap;
+      ap.w_pulled = la.w + o;
+      ap.conf = la.stamp ? sh.conf.as<unsigned char>() + o : nullptr;
+      ap.vsave = sh.vsave.as<float>() + o * (size_t)K;
+      int nl = launch_bwd_update(tt, h->prm, la.slot + o, la.vrow + o, Kseg, &hdr[r]->nkeys, cstart, cstart + 1,
+                                 lay.at<void>(mine, lay.off_occ, lay.str_occ, d, r), valued,
+                                 lay.at<float>(mine, lay.off_p, lay.str_p, d, r),
+                                 lay.at<float>(mine, lay.off_pxv, lay.str_pxv, d, r), flags, 1, &ap, O);
+      if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
+      h->launches += nl;
+      h->launches += launch_initv(h->tab, h->prm, la.slot + o, Kseg, &hdr[r]->nkeys, flags, ws, O);
+    } else {
+      h->launches += launch_penalty(h->prm, sh.src_prog(r), la.w + o, la.vrow + o, h->tab.V, h->tab.rs, 0, Kseg,
+                                    &hdr[r]->nkeys, O);
+    }
+    h->launches += launch_shard_done(sh.src_prog(r), h->tab.prog, lay.at<double>(sh.peer[r], lay.off_pen, lay.str_pen, d, me),
+                                     lay.flag(sh.peer[r], ShardLayout::F_DONE, me), fv, O);
+  }
+  DFB_CUDA(h, cudaEventRecord(sh.ev_upd[d], O));
+
+  // ------------------------------- F: penalties back, Progress snapshot -------------------------------
+  DFB_CUDA(h, cudaStreamWaitEvent(F, sh.ev_reduce[d], 0));
+  if (auc) DFB_CUDA(h, cudaStreamWaitEvent(F, sh.ev_auc[d], 0));
+  DFB_CUDA(h, cudaStreamWaitEvent(F, sh.ev_upd[d], 0));
+  h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_DONE, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, F);
+  h->launches += launch_shard_collect(lay.at<double>(mine, lay.off_pen, lay.str_pen, d, 0), (int)(lay.str_pen / 8), S,
+                                      sh.prog_w(d), h->tab.prog, sh.stage(d), F);
+  if (h->submitted - h->collected == (uint64_t)dfb_engine::kRing) DFB_TRY(dfbh::collect_one(h, &h->backlog));
+  const int rs = (int)(h->submitted % dfb_engine::kRing);
+  DFB_CUDA(h, cudaMemcpyAsync(&h->h_ring[rs], sh.stage(d), sizeof(DevProgress), cudaMemcpyDeviceToHost, F));
+  DFB_CUDA(h, cudaEventRecord(h->ring_done[rs], F));
+  h->submitted++;
+  DFB_CUDA(h, cudaEventRecord(sh.ev_fin[d], F));
+  if (consumed) DFB_CUDA(h, cudaEventRecord(consumed, F));
+  sh.step++;
+  DFB_CUDA(h, cudaGetLastError());
+  return DFB_OK;
+}
+
+}  // namespace
+
+void dfbh::shard_destroy(dfb_engine* h) {
+  ShardState* sh = h->shard;
+  if (!sh) return;
+  if (sh->w_stream) cudaStreamDestroy(sh->w_stream);
+  if (sh->f_stream) cudaStreamDestroy(sh->f_stream);
+  cudaEvent_t* evs[] = {sh->ev_struct, sh->ev_part, sh->ev_reduce, sh->ev_auc, sh->ev_upd, sh->ev_fin};
+  for (auto* e : evs) for (int i = 0; i < 2; ++i) if (e[i]) cudaEventDestroy(e[i]);
+  DevBuf* bufs[] = {&sh->L.keys, &sh->L.lidx, &sh->L.cnt, &sh->L.occ_sorted, &sh->L.col_start, &sh->L.col_end, &sh->L.scal,
+                    &sh->wb, &sh->rowcnt, &sh->pred[0], &sh->pred[1], &sh->slot, &sh->w, &sh->vrow, &sh->wv, &sh->conf,
+                    &sh->vsave, &sh->flags, &sh->ws};
+  for (auto* b : bufs) if (b->p) cudaFree(b->p);
+  if (sh->dprog) cudaFree(sh->dprog);
+  if (sh->mailbox) cudaFree(sh->mailbox);
+  delete sh;
+  h->shard = nullptr;
+}
+
+int dfbh::shard_sync(dfb_engine* h) {
+  ShardState* sh = h->shard;
+  if (!sh) return DFB_OK;
+  DFB_CUDA(h, cudaStreamSynchronize(sh->w_stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->aux_stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  DFB_CUDA(h, cudaStreamSynchronize(sh->f_stream));
+  return DFB_OK;
+}
+
+extern "C" {
+
+int dfb_shard_init(dfb_handle h, int rank, int nranks, size_t max_rows, size_t max_nnz, size_t seg_keys,
+                   size_t seg_nnz, size_t* mailbox_bytes) {
+  if (!h) return DFB_ERR_INVALID;
+  if (h->shard) return h->fail(DFB_ERR_INVALID, "dfb_shard_init was already called");
+  if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return h->fail(DFB_ERR_INVALID, "1 <= nranks <= 8, 0 <= rank < nranks");
+  if (max_rows == 0 || max_nnz == 0 || max_nnz > 0x7fffffffULL || max_rows > 0x7fffffffULL)
+    return h->fail(DFB_ERR_INVALID, "max_rows / max_nnz out of range");
+  const int K = h->prm.V_dim;
+  if (!(fm_fast_supported(K) && h->scatter_sorted && !h->force_generic && h->tab.ks == K))
+    return h->fail(DFB_ERR_INVALID, "the fused sharded store needs V_dim in {8,16,32,64,128} and scatter=sorted "
+                                    "(other configurations: the all_to_all ShardedStore)");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  ShardState* sh = new ShardState();
+  h->shard = sh;
+  sh->rank = rank; sh->S = nranks; sh->Bcap = max_rows; sh->Ncap = max_nnz;
+  // capacity of one (worker, owner) segment: everything for one rank, else twice the even share (skew margin)
+  auto seg_default = [&](size_t total) { return nranks == 1 ? total : std::min(total, 2 * total / (size_t)nranks + 4096); };
+  const size_t Kseg = seg_keys ? std::min(seg_keys, max_nnz) : seg_default(max_nnz);
+  const size_t Nseg = seg_nnz ? std::min(seg_nnz, max_nnz) : seg_default(max_nnz);
+  sh->lay.compute(nranks, K, max_rows, Kseg, Nseg);
+  sh->timeout_cycles = h->shard_timeout_ms * 2000000LL;
+  auto fail = [&](int rc) { dfbh::shard_destroy(h); return rc; };
+  cudaError_t e;
+  if ((e = cudaMalloc(&sh->mailbox, sh->lay.total)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMalloc(shard mailbox)"));
+  if ((e = cudaMemset(sh->mailbox, 0, sh->lay.total)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMemset(shard mailbox)"));
+  sh->peer[rank] = sh->mailbox;
+  if ((e = cudaStreamCreateWithFlags(&sh->w_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
+  if ((e = cudaStreamCreateWithFlags(&sh->f_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
+  cudaEvent_t* evs[] = {sh->ev_struct, sh->ev_part, sh->ev_reduce, sh->ev_auc, sh->ev_upd, sh->ev_fin};
+  for (auto* ev : evs)
+    for (int i = 0; i < 2; ++i)
+      if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaEventCreate"));
+  const size_t tot = (size_t)nranks * Kseg;
+  int rc = 0;
+  if ((rc = h->ensure(sh->wb, sizeof(ShardBounds))) || (rc = h->ensure(sh->slot, tot * 4)) || (rc = h->ensure(sh->w, tot * 4)) ||
+      (rc = h->ensure(sh->vrow, tot * 4)) || (rc = h->ensure(sh->wv, tot * 8)) || (rc = h->ensure(sh->flags, Kseg * 4)) ||
+      (rc = h->ensure(sh->ws, (Kseg / 32 + 64) * 4)))
+    return fail(rc);
+  if (nranks > 1 && ((rc = h->ensure(sh->conf, tot)) || (rc = h->ensure(sh->vsave, tot * (size_t)K * 4)))) return fail(rc);
+  const size_t np = (size_t)nranks + 4;
+  if ((e = cudaMalloc(&sh->dprog, np * sizeof(DevProgress))) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMalloc"));
+  if ((e = cudaMemset(sh->dprog, 0, np * sizeof(DevProgress))) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMemset"));
+  sh->connected = nranks == 1;
+  if (mailbox_bytes) *mailbox_bytes = sh->lay.total;
+  return DFB_OK;
+}
+
+int dfb_shard_export(dfb_handle h, void** mailbox_ptr, unsigned char* handle64) {
+  if (!h || !h->shard) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  if (mailbox_ptr) *mailbox_ptr = h->shard->mailbox;
+  if (handle64) {
+    cudaIpcMemHandle_t mh;
+    DFB_CUDA(h, cudaIpcGetMemHandle(&mh, h->shard->mailbox));
+    memcpy(handle64, &mh, 64);
+  }
+  return DFB_OK;
+}
+
+int dfb_shard_connect(dfb_handle h, void* const* peer_mailbox) {
+  if (!h || !h->shard || !peer_mailbox) return DFB_ERR_INVALID;
+  ShardState& sh = *h->shard;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  for (int s = 0; s < sh.S; ++s) {
+    if (s == sh.rank) continue;
+    if (!peer_mailbox[s]) return h->fail(DFB_ERR_INVALID, "peer mailbox pointer is NULL");
+    sh.peer[s] = peer_mailbox[s];
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, peer_mailbox[s]) == cudaSuccess && at.device != h->device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);     // same-process peers; IPC mappings enabled it already
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return h->cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    }
+    cudaGetLastError();
+  }
+  sh.connected = true;
+  return DFB_OK;
+}
+
+int dfb_shard_step_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint64_t* d_ids,
+                       const float* d_value_or_null, const float* d_label, int push_cnt, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  return shard_step(h, nrows, nnz, d_offset, d_ids, d_value_or_null, d_label, push_cnt, is_train, nullptr, nullptr);
+}
+
+int dfb_shard_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids, const float* value,
+                         const float* label, int push_cnt, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_TRY(dfbh::check_csr(h, nrows, offset));
+  if (nrows && !label) return h->fail(DFB_ERR_INVALID, "label is NULL");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
+  if (nnz && !ids) return h->fail(DFB_ERR_INVALID, "ids is NULL");
+  auto& in = h->in[h->seq & 1];
+  if (!(in.pre_ids == ids && ids && in.pre_nrows == nrows && in.pre_nnz == nnz))
+    DFB_TRY(dfbh::stage_raw(h, in, nrows, nnz, offset, ids, value, label));
+  in.pre_ids = nullptr;
+  int rc = shard_step(h, nrows, nnz, in.off.as<uint64_t>(), in.ids.as<uint64_t>(), value ? in.val.as<float>() : nullptr,
+                      in.lab.as<float>(), push_cnt, is_train, in.copied, in.consumed);
+  h->seq++;
+  return rc;
+}
+
+int dfb_shard_info(dfb_handle h, int* rank, int* nranks, size_t* seg_keys, size_t* seg_nnz, uint64_t* steps) {
+  if (!h || !h->shard) return DFB_ERR_INVALID;
+  if (rank) *rank = h->shard->rank;
+  if (nranks) *nranks = h->shard->S;
+  if (seg_keys) *seg_keys = h->shard->lay.Kseg;
+  if (seg_nnz) *seg_nnz = h->shard->lay.Nseg;
+  if (steps) *steps = h->shard->step;
+  return DFB_OK;
+}
+
+}  // extern "C"

@@ -308,6 +308,48 @@ class PeerShardedStore(ShardedStore):
         self._mark("owner_update")
 
 
+class FusedShardedStore:
+    """The NVLink-sharded store behind the C-ABI (dfb_shard_*, csrc/shard.cu + kernels_shard.cu): the product's
+    multi-GPU path.  Unlike ShardedStore / PeerShardedStore above (which move the k-wide rows of the active keys
+    to the workers and the gradient rows back, Store::Pull / Push as the reference's ps-lite does), the rows stay
+    on their owner: owners compute the partial FM interaction sums of every worker's rows and ship (k+2) floats
+    per EXAMPLE; the whole protocol (GPU localizer, slicing, peer stores, step-counter flags) runs on the
+    device.  This class only does the plumbing a host has to do once: exchange the mailbox handles (CUDA IPC,
+    one process per GPU) through torch.distributed, or wire engines of the same process together."""
+
+    def __init__(self, engine, max_rows, max_nnz, group=None, seg_keys=0, seg_nnz=0):
+        self.E = engine
+        self.group = group
+        self.S = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.mailbox_bytes = engine.shard_init(self.rank, self.S, int(max_rows), int(max_nnz), int(seg_keys), int(seg_nnz))
+        ptr, handle = engine.shard_export()
+        if self.S > 1:
+            handles = [None] * self.S
+            dist.all_gather_object(handles, handle, group=group)
+            peers = [ptr if r == self.rank else engine.peer_open(handles[r]) for r in range(self.S)]
+            engine.shard_connect(peers)
+            dist.barrier(group=group)      # nobody starts storing into a mailbox that is not mapped everywhere yet
+
+    @staticmethod
+    def connect_local(engines, max_rows, max_nnz, seg_keys=0, seg_nnz=0):
+        """N engines of ONE process (one per GPU, or several on one GPU in tests): rank = position in the list"""
+        S = len(engines)
+        for r, E in enumerate(engines):
+            E.shard_init(r, S, int(max_rows), int(max_nnz), int(seg_keys), int(seg_nnz))
+        ptrs = [E.shard_export()[0] for E in engines]
+        for E in engines:
+            E.shard_connect(ptrs)
+
+    def step_dev(self, nrows, nnz, d_off, d_ids, d_val, d_lab, is_train=True, push_cnt=False):
+        """collective: one minibatch of raw CSR<uint64> per rank, arrays already on this rank's GPU"""
+        self.E.shard_step_dev(nrows, nnz, d_off, d_ids, d_val, d_lab, push_cnt, is_train)
+
+    def step_host(self, nrows, off, ids, val, lab, is_train=True, push_cnt=False):
+        """collective: the same from (pinned) host arrays; H2D is double-buffered against the previous step"""
+        self.E.shard_step_async(nrows, off, ids, val, lab, push_cnt, is_train)
+
+
 # ---------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): one process per GPU, launched by torch.distributed.run
 # ---------------------------------------------------------------------------------------------

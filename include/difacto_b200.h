@@ -40,7 +40,8 @@ typedef enum {
   DFB_ERR_CUDA = -2,      /* CUDA runtime error */
   DFB_ERR_CAPACITY = -3,  /* key table or V-row pool exhausted */
   DFB_ERR_PARAM = -4,     /* parameter missing / out of range (dmlc::ParamError in the reference) */
-  DFB_ERR_NCCL = -5
+  DFB_ERR_NCCL = -5,
+  DFB_ERR_TIMEOUT = -6    /* a rank of the sharded store did not show up within shard_timeout_ms */
 } dfb_status;
 
 /* value types of Store::Push / Pull: include/difacto/store.h:33-35 */
@@ -73,6 +74,13 @@ typedef struct {
  *                         row order per key like SpMM::TransTimes); atomic = fp32 red.global scatter
  *                         into dense gradient rows followed by a separate update kernel
  *   overlap_auc (1)       run the AUC kernels on an auxiliary stream, overlapped with the update
+ *   l2_hints (1)          per-load L2 eviction policies in the gather kernels (V rows evict_first, the per-nnz
+ *                         {w, row index} view evict_last)
+ *   id_bits (0)           > 0: feature ids are < 2^id_bits; fixes the bit range the GPU localizer's radix sort
+ *                         visits.  0: the range is learned from the first raw batch (one 8-byte sync) and
+ *                         verified on the device afterwards; a later batch with wider ids is dropped with
+ *                         DFB_ERR_INVALID (pass id_bits, or use the synchronous dfb_train_step_raw)
+ *   shard_timeout_ms (20000)  how long a rank of the sharded store waits for a peer
  *   force_generic (0)     1 = use the any-V_dim kernels even where a specialised one exists (tests)
  * Keys that are neither are returned through dfb_unknown_kwarg, mirroring the
  * "return the unconsumed kwargs" convention (updater.h:34, main.cc:25-31).
@@ -284,6 +292,40 @@ int dfb_dev_fm_step_peer(dfb_handle h, size_t nrows, size_t nnz, const uint64_t*
                          size_t nkeys, const float* d_w, const int* d_hasv, const float* d_V, int nseg,
                          const size_t* seg_bounds, float* const* peer_gw, float* const* peer_gV,
                          int first_seg /* segment to start with (own rank): staggers peer traffic */);
+
+/* ---------------------------------------------------------------------------------
+ * The NVLink-sharded store behind the C-ABI: N engines (one per GPU; one process per GPU with CUDA IPC, or
+ * N threads of one process) form one model, rank r owning the r-th range of the reversed key space exactly
+ * like ps-lite's servers (postoffice.cc:127-136).  It replaces, for this path, the worker/server exchange of
+ * the reference (SGDLearner's workers calling Store::Pull / Push on KVWorker, the servers running
+ * SGDUpdater; src/sgd/sgd_learner.cc:78-89,138-177, ps-lite/include/ps/kv_app.h:406-460).
+ * Every rank calls dfb_shard_step_* once per minibatch, COLLECTIVELY (same number of calls, same push_cnt /
+ * is_train; a rank that ran out of data passes nrows = 0).  A step is bulk-synchronous like the
+ * all_to_all protocol of dfb_dev_*: every worker's forward sees the model after all updates of the previous
+ * step; an owner applies the workers' gradients as separate Updates in rank order (sgd_updater.cc:74-98),
+ * each taken at the V the worker "pulled" at step start.  What crosses NVLink is not the k-wide rows but the
+ * per-example partial interaction sums (see csrc/kernels_shard.cu); nothing is synchronised with the host.
+ *   dfb_shard_init     allocate this rank's mailbox (capacity: max_rows x max_nnz per minibatch; seg_keys /
+ *                      seg_nnz = capacity of one (worker, owner) key segment, 0 = twice the even share)
+ *   dfb_shard_export   the mailbox pointer (peers in the same process) and its CUDA IPC handle (peers in
+ *                      other processes open it with dfb_peer_open)
+ *   dfb_shard_connect  the peers' mailbox pointers, indexed by rank (entry [rank] is ignored)
+ *   dfb_shard_step_dev   one minibatch of raw CSR<uint64> already on the device (enqueue only)
+ *   dfb_shard_step_async the same from host buffers (pinned: asynchronous), double-buffered like
+ *                        dfb_train_step_raw_async; dfb_prefetch_raw may stage the next batch early
+ * Results: dfb_wait_step (per step) / dfb_read_progress (accumulated), as for the other async entry points;
+ * Progress is this rank's own minibatch (loss, AUC, penalty of the weights it used).  DFB_ERR_TIMEOUT: a peer
+ * did not reach the step within shard_timeout_ms (kwarg, default 20000).
+ * ------------------------------------------------------------------------------- */
+int dfb_shard_init(dfb_handle h, int rank, int nranks, size_t max_rows, size_t max_nnz, size_t seg_keys,
+                   size_t seg_nnz, size_t* mailbox_bytes_out);
+int dfb_shard_export(dfb_handle h, void** mailbox_ptr, unsigned char* handle64);
+int dfb_shard_connect(dfb_handle h, void* const* peer_mailbox);
+int dfb_shard_step_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint64_t* d_ids,
+                       const float* d_value_or_null, const float* d_label, int push_cnt, int is_train);
+int dfb_shard_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                         const float* value_or_null, const float* label, int push_cnt, int is_train);
+int dfb_shard_info(dfb_handle h, int* rank, int* nranks, size_t* seg_keys, size_t* seg_nnz, uint64_t* steps);
 
 /* the CUDA stream (cudaStream_t) the handle enqueues on, for event interop with torch */
 void* dfb_stream(dfb_handle h);

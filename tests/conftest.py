@@ -1,6 +1,10 @@
 import os
 import sys
 
+# several engines of one process share a GPU in the sharded-store tests: give every stream its own hardware queue
+# (must be in the environment before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import pytest
 
@@ -13,6 +17,24 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _cuda_usable():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """a plain `pytest` on a box without a usable GPU skips the gpu-marked tests instead of failing in dfb_create"""
+    if _cuda_usable():
+        return
+    skip = pytest.mark.skip(reason="no usable CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")
