@@ -36,7 +36,7 @@ EXPORTS = [
     "dfb_dev_fm_step_peer", "dfb_localize", "dfb_train_step_raw", "dfb_train_step_raw_async",
     "dfb_train_step_raw_dev", "dfb_prefetch_raw", "dfb_snapshot_size", "dfb_snapshot", "dfb_restore",
     "dfb_shard_init", "dfb_shard_export", "dfb_shard_connect", "dfb_shard_step_dev", "dfb_shard_step_async",
-    "dfb_shard_info",
+    "dfb_shard_info", "dfb_shard_begin_async", "dfb_shard_phase", "dfb_time_mark", "dfb_time_elapsed_ms",
 ]
 
 _LIB = None
@@ -105,6 +105,10 @@ def lib():
         L.dfb_shard_connect.argtypes = [vp, vp]
         L.dfb_shard_step_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, C.c_int, C.c_int]
         L.dfb_shard_step_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_time_mark.argtypes = [vp, C.c_int]
+        L.dfb_time_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.dfb_shard_begin_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_shard_phase.argtypes = [vp, C.c_int]
         L.dfb_shard_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz), C.POINTER(sz),
                                      C.POINTER(u64)]
         L.dfb_stream.restype = vp
@@ -324,12 +328,23 @@ class Engine:
     def profile(self, enable=True):
         self._ck(self.L.dfb_profile(self.h, int(enable)))
 
+    STAGES = ["lookup", "fm", "auc", "csc", "update", "localize", "shard_slice_scatter", "shard_owner_partials",
+              "shard_worker_reduce", "shard_owner_updates"]
+
     def profile_read(self):
-        ms = np.zeros(5, np.float64)
-        cnt = np.zeros(5, np.uint64)
+        ns = len(self.STAGES)       # DFB_NUM_STAGES
+        ms = np.zeros(ns, np.float64)
+        cnt = np.zeros(ns, np.uint64)
         self._ck(self.L.dfb_profile_read(self.h, _p(ms), _p(cnt)))
-        names = ["lookup", "fm", "auc", "csc", "update"]
-        return {n: dict(ms=float(ms[i]), count=int(cnt[i])) for i, n in enumerate(names)}
+        return {n: dict(ms=float(ms[i]), count=int(cnt[i])) for i, n in enumerate(self.STAGES)}
+
+    def time_mark(self, which):
+        self._ck(self.L.dfb_time_mark(self.h, int(which)))
+
+    def time_elapsed_ms(self):
+        ms = C.c_float()
+        self._ck(self.L.dfb_time_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def read_progress(self):
         pr = Progress()
@@ -420,6 +435,13 @@ class Engine:
     def shard_step_async(self, nrows, offset, ids, value, label, push_cnt=False, is_train=True):
         self._ck(self.L.dfb_shard_step_async(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label),
                                              int(push_cnt), int(is_train)))
+
+    def shard_begin_async(self, nrows, offset, ids, value, label, push_cnt=False, is_train=True):
+        self._ck(self.L.dfb_shard_begin_async(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label),
+                                              int(push_cnt), int(is_train)))
+
+    def shard_phase(self, phase):
+        self._ck(self.L.dfb_shard_phase(self.h, int(phase)))
 
     def shard_info(self):
         r, n = C.c_int(), C.c_int()

@@ -66,6 +66,21 @@ __device__ __forceinline__ float pen_w(const Params& p, float w) {
   return p.l1 * fabsf(w) + 0.5f * p.l2 * w * w;
 }
 
+// one 32-byte table entry fetched with ONE 256-bit request (LDG.256, sm_100), L2-only so that an entry another
+// thread of the same launch just inserted is never served stale from L1
+struct Entry256 {
+  unsigned long long key, q1, q2, q3;      // {key | vrow, pad | fea_cnt, w | sqrt_g, z}
+  __device__ __forceinline__ int vrow() const { return (int)(unsigned)(q1 & 0xffffffffULL); }
+  __device__ __forceinline__ float w() const { return __uint_as_float((unsigned)(q2 >> 32)); }
+};
+__device__ __forceinline__ Entry256 load_entry(const Entry* p) {
+  Entry256 e;
+  asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(e.key), "=l"(e.q1), "=l"(e.q2), "=l"(e.q3)
+               : "l"(p));
+  return e;
+}
+
 // model_[key] (sgd_updater.cc:43-45,65-67,86-88): find or default-construct.  Returns the slot or -1.
 // On a hit (or a fresh insert) *lo receives the first half of the entry {key, vrow, pad} as loaded.
 template <bool INSERT>

@@ -149,9 +149,13 @@ void to_public(const DevProgress& d, dfb_progress* out) {
   out->nnz_w = 0.f; out->nrows = (float)d.nrows; out->new_keys = d.new_keys; out->new_vrows = d.new_vrows;
 }
 
-int prof_drain(dfb_engine* h) {
+}  // namespace
+
+int dfbh::prof_drain(dfb_engine* h) {
   if (h->pev.empty()) return 0;
   DFB_CUDA(h, cudaStreamSynchronize(h->stream));
+  DFB_CUDA(h, cudaStreamSynchronize(h->loc_stream));
+  if (h->shard) DFB_TRY(dfbh::shard_sync(h));
   for (int r = 0; r < dfb_engine::kProfRing; ++r)
     for (int st = 0; st < dfb_engine::kStages; ++st) {
       char& used = h->pev_used[r * dfb_engine::kStages + st];
@@ -163,21 +167,9 @@ int prof_drain(dfb_engine* h) {
     }
   return 0;
 }
+using dfbh::prof_drain;
 
-struct StageTimer {
-  dfb_engine* h; int st; cudaEvent_t* e = nullptr;
-  StageTimer(dfb_engine* h_, int st_) : h(h_), st(st_) {
-    if (!h->profile) return;
-    const int r = (int)(h->prof_steps % dfb_engine::kProfRing);
-    e = &h->pev[(r * dfb_engine::kStages + st) * 2];
-    cudaEventRecord(e[0], h->stream);
-  }
-  ~StageTimer() {
-    if (!e) return;
-    cudaEventRecord(e[1], h->stream);
-    h->pev_used[((h->prof_steps % dfb_engine::kProfRing)) * dfb_engine::kStages + st] = 1;
-  }
-};
+namespace {
 
 // the fused minibatch on device-resident inputs (everything enqueued on h->stream)
 int ensure_sorted_ws(dfb_engine* h, size_t nrows, size_t nnz, size_t U, bool valued, bool csc_given = false) {
@@ -321,7 +313,7 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
     h->launches += launch_penalty(h->prm, h->tab.prog, u_w, u_vrow, h->tab.V, h->tab.rs, 0, U, dU, s);
   }
   if (h->profile) {
-    tm_upd.~StageTimer(); tm_upd.e = nullptr;
+    tm_upd.stop();
     h->prof_steps++;
   }
   if (auc_pending) DFB_CUDA(h, cudaStreamWaitEvent(s, h->ev_auc_done, 0));
@@ -446,7 +438,11 @@ int step_raw_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off,
   if (L.used) DFB_CUDA(h, cudaStreamWaitEvent(ls, L.consumed, 0));
   const bool dev_count_ok = !h->force_generic && fm_fast_supported(h->prm.V_dim) && (!is_train || h->scatter_sorted);
   size_t U = 0;
-  DFB_TRY(localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, L, ls, !dev_count_ok, exact_range, &U));   // Localizer(-1, ...), sgd_learner.cc:203
+  if (h->profile && h->prof_steps && h->prof_steps % dfb_engine::kProfRing == 0) DFB_TRY(prof_drain(h));
+  {
+    StageTimer tm(h, 5, ls);
+    DFB_TRY(localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, L, ls, !dev_count_ok, exact_range, &U));   // Localizer(-1, ...), sgd_learner.cc:203
+  }
   const float* d_cnt = nullptr;
   const int* cnt_cols = nullptr;
   if (push_cnt && U) {
@@ -533,6 +529,8 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
       l2_fetch = (int)x;
     }
     else if (k == "overlap_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->overlap_auc = (int)x; }
+    else if (k == "lookup_ilp") { if (!need_int(1, 4)) { delete h; return DFB_ERR_PARAM; } g_lookup_ilp = (int)x; }
+    else if (k == "lookup_ctas") { if (!need_int(1, 64)) { delete h; return DFB_ERR_PARAM; } g_lookup_ctas = (int)x; }
     else if (k == "l2_hints") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->l2_hints = (int)x; }
     else if (k == "id_bits") { if (!need_int(0, 64)) { delete h; return DFB_ERR_PARAM; } h->id_bits = (int)x; }
     else if (k == "shard_timeout_ms") { if (!need_int(1, 3600000)) { delete h; return DFB_ERR_PARAM; } h->shard_timeout_ms = x; }
@@ -646,6 +644,9 @@ int dfb_destroy(dfb_handle h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_fm_done) cudaEventDestroy(h->ev_fm_done);
   if (h->ev_auc_done) cudaEventDestroy(h->ev_auc_done);
   delete h;
@@ -999,6 +1000,40 @@ int dfb_wait_step(dfb_handle h, dfb_progress* out) {
   if (out) to_public(one, out);
   *h->h_prog = one;
   return check_dev_err(h);
+}
+
+}  // extern "C"
+int dfbh::join_streams(dfb_engine* h) {
+  if (!h->ev_join) DFB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  cudaStream_t others[] = {h->copy_stream, h->aux_stream, h->loc_stream};
+  for (cudaStream_t o : others) {
+    DFB_CUDA(h, cudaEventRecord(h->ev_join, o));
+    DFB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  }
+  return 0;
+}
+extern "C" {
+
+int dfb_time_mark(dfb_handle h, int which) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->ev_t0) { DFB_CUDA(h, cudaEventCreate(&h->ev_t0)); DFB_CUDA(h, cudaEventCreate(&h->ev_t1)); }
+  if (which == 0) {
+    DFB_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
+  } else {
+    if (h->shard) DFB_TRY(dfbh::shard_sync(h));       // the shard's streams: drained (its last event is on another stream)
+    DFB_TRY(dfbh::join_streams(h));
+    DFB_CUDA(h, cudaEventRecord(h->ev_t1, h->stream));
+  }
+  return DFB_OK;
+}
+
+int dfb_time_elapsed_ms(dfb_handle h, float* ms) {
+  if (!h || !ms || !h->ev_t0) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  DFB_CUDA(h, cudaEventSynchronize(h->ev_t1));
+  DFB_CUDA(h, cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+  return DFB_OK;
 }
 
 int dfb_profile(dfb_handle h, int enable) {

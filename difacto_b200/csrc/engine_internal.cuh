@@ -76,14 +76,17 @@ struct dfb_engine {
   uint64_t submitted = 0, collected = 0;
   dfb::DevProgress backlog;             // snapshots folded in when the ring was full
   // optional per-stage CUDA-event timing (bench.py's roofline numbers)
-  static constexpr int kStages = 5;      // lookup+pull, fm, auc, csc sort, update(+initv)
+  // 0 lookup+pull, 1 fm, 2 auc, 3 csc sort, 4 update(+initv), 5 GPU localizer (raw batches),
+  // sharded store: 6 worker slice+scatter, 7 owner lookup+partial sums, 8 worker reduce, 9 owner updates
+  static constexpr int kStages = DFB_NUM_STAGES;
   static constexpr int kProfRing = 32;
   int profile = 0;
   std::vector<cudaEvent_t> pev;          // [kProfRing][kStages][2]
   std::vector<char> pev_used;            // [kProfRing][kStages]
   uint64_t prof_steps = 0;
-  double stage_ms[kStages] = {0, 0, 0, 0, 0};
-  uint64_t stage_n[kStages] = {0, 0, 0, 0, 0};
+  double stage_ms[kStages] = {};
+  uint64_t stage_n[kStages] = {};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_join = nullptr;   // dfb_time_mark
   dfb::DevProgress* h_prog = nullptr;   // pinned
   unsigned long long* h_nvals = nullptr;  // pinned
   ShardState* shard = nullptr;          // the NVLink-sharded store this engine is a rank of (shard.cu)
@@ -108,8 +111,28 @@ struct dfb_engine {
     if (_rc != 0) return _rc;      \
   } while (0)
 
+// CUDA-event pair around one stage of a step (only while dfb_profile is on), on the stream the stage runs on
+struct StageTimer {
+  dfb_engine* h; int st; cudaStream_t s; cudaEvent_t* e = nullptr;
+  StageTimer(dfb_engine* h_, int st_, cudaStream_t s_ = nullptr) : h(h_), st(st_), s(s_ ? s_ : h_->stream) {
+    if (!h->profile) return;
+    const int r = (int)(h->prof_steps % dfb_engine::kProfRing);
+    e = &h->pev[(r * dfb_engine::kStages + st) * 2];
+    cudaEventRecord(e[0], s);
+  }
+  void stop() {
+    if (!e) return;
+    cudaEventRecord(e[1], s);
+    h->pev_used[((h->prof_steps % dfb_engine::kProfRing)) * dfb_engine::kStages + st] = 1;
+    e = nullptr;
+  }
+  ~StageTimer() { stop(); }
+};
+
 // host-side helpers defined in engine.cu and used by shard.cu
 namespace dfbh {
+int prof_drain(dfb_engine* h);
+int join_streams(dfb_engine* h);        // make the main stream wait for everything enqueued on the others
 int ensure_key_ws(dfb_engine* h, size_t n);
 // Localizer::Compact on the device into L (no host synchronisation unless need_host_U):
 //   *U_out = the unique-key count when need_host_U, else the capacity (nnz); L.dU() holds the count on the device

@@ -319,14 +319,13 @@ __global__ void __launch_bounds__(256) k_shard_reduce(ReduceArgs a) {
 // once per worker in rank order, and the later ones need its pull-time V (k_shard_conflicts).
 template <bool INSERT>
 __global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a) {
-  constexpr int ILP = 4;
+  constexpr int ILP = 2;
   const size_t total = (size_t)a.S * a.Kseg;
   const size_t tile = (size_t)blockDim.x * ILP;
   for (size_t base = (size_t)blockIdx.x * tile; base < total; base += (size_t)gridDim.x * tile) {
     unsigned long long key[ILP];
     uint64_t h[ILP];
-    int4 lo[ILP];
-    float4 hi[ILP];
+    Entry256 e[ILP];
     bool valid[ILP];
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
@@ -339,10 +338,7 @@ __global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a) {
     }
 #pragma unroll
     for (int q = 0; q < ILP; ++q)
-      if (valid[q]) {
-        lo[q] = __ldcg(reinterpret_cast<const int4*>(&t.tab[h[q]]));
-        hi[q] = __ldcg(reinterpret_cast<const float4*>(&t.tab[h[q]].fea_cnt));
-      }
+      if (valid[q]) e[q] = load_entry(&t.tab[h[q]]);
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
       if (!valid[q]) continue;
@@ -352,9 +348,8 @@ __global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a) {
       if (key[q] == kEmptyKey) {
         raise_err(t.prog, DFB_ERR_INVALID);
       } else {
-        const unsigned long long cur = ((unsigned long long)(unsigned)lo[q].y << 32) | (unsigned long long)(unsigned)lo[q].x;
-        if (cur == key[q]) {
-          slot = (int)h[q]; w = hi[q].y; vr = lo[q].z;
+        if (e[q].key == key[q]) {
+          slot = (int)h[q]; w = e[q].w(); vr = e[q].vrow();
         } else {
           slot = table_find<INSERT>(t, key[q], h[q]);
           if (slot >= 0) { w = t.tab[slot].w; vr = t.tab[slot].vrow; }
@@ -511,7 +506,7 @@ int launch_shard_reduce(int V_dim, const ReduceArgs& a, cudaStream_t s) {
 
 int launch_shard_lookup(Table& t, const LookupArgs& a, bool insert, cudaStream_t s) {
   const size_t total = (size_t)a.S * a.Kseg;
-  const int grid = grid_cap(total, 256 * 4, 148 * 8);
+  const int grid = grid_cap(total, 256 * 2, 148 * 64);
   if (insert) k_shard_lookup<true><<<grid, 256, 0, s>>>(t, a);
   else        k_shard_lookup<false><<<grid, 256, 0, s>>>(t, a);
   return 1;

@@ -47,19 +47,17 @@ __global__ void k_table_init(Entry* tab, uint64_t cap, TableState* st, DevProgre
 // bound, so every thread keeps ILP independent first probes in flight (both halves of the entry are
 // fetched with the probe; a hit needs no second round trip) and only collisions fall back to the
 // serial probe loop.
-template <bool INSERT>
+template <bool INSERT, int ILP>
 __global__ void __launch_bounds__(256) k_lookup(Table t, const uint64_t* __restrict__ keys, size_t n_cap,
                                                 const unsigned long long* __restrict__ dn,
                                                 int* __restrict__ slot_out, float* __restrict__ w_out,
                                                 int* __restrict__ vrow_out, int2* __restrict__ wv_out) {
-  constexpr int ILP = 4;
   const size_t n = dev_count(n_cap, dn);
   const size_t tile = (size_t)blockDim.x * ILP;
   for (size_t base = (size_t)blockIdx.x * tile; base < n; base += (size_t)gridDim.x * tile) {
     unsigned long long key[ILP];
     uint64_t h[ILP];
-    int4 lo[ILP];
-    float4 hi[ILP];
+    Entry256 e[ILP];
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
       const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
@@ -69,11 +67,7 @@ __global__ void __launch_bounds__(256) k_lookup(Table t, const uint64_t* __restr
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
       const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
-      if (i < n) {
-        // L2-only loads: an entry inserted by another thread of this launch must not be served stale from L1
-        lo[q] = __ldcg(reinterpret_cast<const int4*>(&t.tab[h[q]]));
-        hi[q] = __ldcg(reinterpret_cast<const float4*>(&t.tab[h[q]].fea_cnt));
-      }
+      if (i < n) e[q] = load_entry(&t.tab[h[q]]);
     }
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
@@ -84,9 +78,8 @@ __global__ void __launch_bounds__(256) k_lookup(Table t, const uint64_t* __restr
       if (key[q] == kEmptyKey) {
         raise(t.prog, DFB_ERR_INVALID);
       } else {
-        const unsigned long long cur = ((unsigned long long)(unsigned)lo[q].y << 32) | (unsigned long long)(unsigned)lo[q].x;
-        if (cur == key[q]) {
-          slot = (int)h[q]; w = hi[q].y; vr = lo[q].z;
+        if (e[q].key == key[q]) {
+          slot = (int)h[q]; w = e[q].w(); vr = e[q].vrow();
         } else {
           slot = table_find<INSERT>(t, key[q], h[q]);
           if (slot >= 0 && w_out) { w = t.tab[slot].w; vr = t.tab[slot].vrow; }
@@ -148,7 +141,10 @@ __device__ __forceinline__ int rand_r_dev(unsigned* seed) {
 }
 
 // ---- ranks of the flagged keys without a host-known count: counts per tile of 32 keys, one-CTA
-// exclusive scan over the tiles, rank inside the tile from a ballot.  ws[0..1] = total (u64), ws[2+t] = tile t ----
+// exclusive scan over the tiles, rank inside the tile from a ballot.
+// ws[0..1] = total (u64), ws[2] = "any flag set" (the usual answer is no: everything after the count is skipped),
+// ws[4 + t] = tile t ----
+constexpr int kTileBase = 4;
 __global__ void k_flag_tiles(const int* __restrict__ flags, size_t n_cap, const unsigned long long* __restrict__ dn,
                              int* __restrict__ ws) {
   const size_t n = dev_count(n_cap, dn);
@@ -159,23 +155,31 @@ __global__ void k_flag_tiles(const int* __restrict__ flags, size_t n_cap, const 
   for (size_t tl = warp0; tl < ntiles; tl += nwarps) {
     const size_t i = tl * 32 + lane;
     const unsigned m = __ballot_sync(kFull, i < n && flags[i] != 0);
-    if (lane == 0) ws[2 + tl] = __popc(m);
+    if (lane == 0) {
+      ws[kTileBase + tl] = __popc(m);
+      if (m) atomicOr(&ws[2], 1);
+    }
   }
 }
 
+// 8 consecutive tiles per thread, 8192 per iteration of the block
 __global__ void __launch_bounds__(1024) k_tile_scan(int* __restrict__ ws, size_t n_cap,
                                                     const unsigned long long* __restrict__ dn) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
+  if (ws[2] == 0) return;          // nothing flagged: total stays 0
   const size_t n = dev_count(n_cap, dn);
   const size_t ntiles = (n + 31) / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int* tiles = ws + kTileBase;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  for (size_t b0 = 0; b0 < ntiles; b0 += blockDim.x) {
-    const size_t i = b0 + threadIdx.x;
-    const int v = i < ntiles ? ws[2 + i] : 0;
-    int x = v;
+  for (size_t b0 = 0; b0 < ntiles; b0 += (size_t)blockDim.x * 8) {
+    const size_t i0 = b0 + (size_t)threadIdx.x * 8;
+    int v[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = i0 + q < ntiles ? tiles[i0 + q] : 0; sum += v[q]; }
+    int x = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(kFull, x, o);
@@ -194,8 +198,12 @@ __global__ void __launch_bounds__(1024) k_tile_scan(int* __restrict__ ws, size_t
     }
     __syncthreads();
     const int carry = s_carry;
-    const int excl = carry + (wid ? s_warp[wid - 1] : 0) + (x - v);
-    if (i < ntiles) ws[2 + i] = excl;
+    int run = carry + (wid ? s_warp[wid - 1] : 0) + (x - sum);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (i0 + q < ntiles) tiles[i0 + q] = run;
+      run += v[q];
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_carry = carry + s_warp[31];
     __syncthreads();
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(int* __restrict__ ws, size_t
 __global__ void k_initv(Table t, Params p, const int* __restrict__ slot, size_t n_cap,
                         const unsigned long long* __restrict__ dn, const int* __restrict__ flags,
                         const int* __restrict__ ws) {
+  if (ws[2] == 0) return;          // no key was flagged
   const size_t n = dev_count(n_cap, dn);
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -220,7 +229,7 @@ __global__ void k_initv(Table t, Params p, const int* __restrict__ slot, size_t 
     unsigned m = m0;
     const unsigned long long vbase = t.state->n_vrows;
     const unsigned seed0 = t.state->seed;
-    const unsigned long long tile_first = (unsigned long long)ws[2 + (base >> 5)];
+    const unsigned long long tile_first = (unsigned long long)ws[kTileBase + (base >> 5)];
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
@@ -954,6 +963,9 @@ inline int grid_warps(size_t nwarps_needed, int warps_per_block, int cap) {
 
 }  // namespace
 
+// tuning knobs of k_lookup (engine kwargs lookup_ilp / lookup_ctas; process-wide)
+int g_lookup_ilp = 2, g_lookup_ctas = 64;
+
 int launch_table_init(Table& t, unsigned seed, cudaStream_t s) {
   k_table_init<<<148 * 8, 256, 0, s>>>(t.tab, t.cap, t.state, t.prog, seed);
   return 1;
@@ -962,9 +974,15 @@ int launch_table_init(Table& t, unsigned seed, cudaStream_t s) {
 int launch_lookup(Table& t, const uint64_t* keys, size_t n, const unsigned long long* dn, bool insert,
                   int* slot_out, float* w_out, int* vrow_out, int2* wv_out, cudaStream_t s) {
   if (n == 0) return 0;
-  const int grid = grid_for(n, 256 * 4, 148 * 8);
-  if (insert) k_lookup<true><<<grid, 256, 0, s>>>(t, keys, n, dn, slot_out, w_out, vrow_out, wv_out);
-  else        k_lookup<false><<<grid, 256, 0, s>>>(t, keys, n, dn, slot_out, w_out, vrow_out, wv_out);
+  const int ilp = g_lookup_ilp;
+  const int grid = grid_for(n, 256 * ilp, 148 * g_lookup_ctas);
+#define DFB_LK(I)                                                                                            \
+  do {                                                                                                       \
+    if (insert) k_lookup<true, I><<<grid, 256, 0, s>>>(t, keys, n, dn, slot_out, w_out, vrow_out, wv_out);   \
+    else        k_lookup<false, I><<<grid, 256, 0, s>>>(t, keys, n, dn, slot_out, w_out, vrow_out, wv_out);  \
+  } while (0)
+  if (ilp == 1) DFB_LK(1); else if (ilp == 2) DFB_LK(2); else DFB_LK(4);
+#undef DFB_LK
   return 1;
 }
 
@@ -985,6 +1003,7 @@ int launch_initv(Table& t, const Params& p, const int* slot, size_t n, const uns
                  int* ws, cudaStream_t s) {
   if (n == 0 || p.V_dim == 0) return 0;
   const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);
+  cudaMemsetAsync(ws, 0, 16, s);
   k_flag_tiles<<<grid, 256, 0, s>>>(flags, n, dn, ws);
   k_tile_scan<<<1, 1024, 0, s>>>(ws, n, dn);
   k_initv<<<grid, 256, 0, s>>>(t, p, slot, n, dn, flags, ws);

@@ -42,6 +42,20 @@ struct ShardState {
   DevBuf slot, w, vrow, wv, conf, vsave, flags, ws;
   DevProgress* dprog = nullptr;   // device: [0,S) per-worker scratch, [S,S+2) worker Progress by parity, [S+2,S+4) staging
   long long timeout_cycles = 0;
+  // the step being enqueued (dfb_shard_begin_* .. dfb_shard_phase(4))
+  struct Ctx {
+    bool open = false;
+    int next_phase = 0;
+    size_t nrows = 0, nnz = 0;
+    const uint64_t* d_off = nullptr;
+    const uint64_t* d_ids = nullptr;
+    const float* d_val = nullptr;
+    const float* d_lab = nullptr;
+    int push_cnt = 0, is_train = 0;
+    cudaEvent_t inputs_ready = nullptr, consumed = nullptr;
+    LookupArgs la;
+    bool auc = false;
+  } cx;
   DevProgress* src_prog(int r) { return dprog + r; }
   DevProgress* prog_w(int d) { return dprog + S + d; }
   DevProgress* stage(int d) { return dprog + S + 2 + d; }
@@ -49,16 +63,43 @@ struct ShardState {
 
 namespace {
 
-int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
-               const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready,
-               cudaEvent_t consumed) {
+int shard_begin(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
+                const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready,
+                cudaEvent_t consumed) {
   ShardState* shp = h->shard;
   if (!shp) return h->fail(DFB_ERR_INVALID, "dfb_shard_init was not called");
   ShardState& sh = *shp;
   if (!sh.connected) return h->fail(DFB_ERR_INVALID, "dfb_shard_connect was not called");
+  if (sh.cx.open) return h->fail(DFB_ERR_INVALID, "the previous sharded step was not finished (dfb_shard_phase 0..4)");
   if (nrows > sh.Bcap || nnz > sh.Ncap) return h->fail(DFB_ERR_CAPACITY, "batch larger than dfb_shard_init's max_rows / max_nnz");
   if (is_train && !h->has_aux) return h->fail(DFB_ERR_INVALID, "no aux data");   // CHECK(has_aux_), sgd_updater.cc:75
   if (nrows && !d_lab) return h->fail(DFB_ERR_INVALID, "label is NULL");
+  ShardState::Ctx& c = sh.cx;
+  c.open = true; c.next_phase = 0;
+  c.nrows = nrows; c.nnz = nnz; c.d_off = d_off; c.d_ids = d_ids; c.d_val = d_val; c.d_lab = d_lab;
+  c.push_cnt = push_cnt; c.is_train = is_train; c.inputs_ready = inputs_ready; c.consumed = consumed;
+  c.auc = h->compute_auc && nrows;
+  return DFB_OK;
+}
+
+// one of the five enqueue phases of a step (see the file header): 0 = W part 1, 1 = O part 1, 2 = W part 2 (+AUC),
+// 3 = O part 2, 4 = F.  A host thread that drives several engines of ONE device must interleave the phases
+// (phase p of every engine before phase p+1 of any), so that every wait refers to work enqueued earlier.
+int shard_phase(dfb_engine* h, int phase) {
+  ShardState* shp = h->shard;
+  if (!shp || !shp->cx.open) return h->fail(DFB_ERR_INVALID, "no sharded step in progress (dfb_shard_begin_*)");
+  ShardState& sh = *shp;
+  ShardState::Ctx& c = sh.cx;
+  if (phase != c.next_phase) return h->fail(DFB_ERR_INVALID, "dfb_shard_phase: phases must be called in order 0..4");
+  c.next_phase++;
+  const size_t nrows = c.nrows, nnz = c.nnz;
+  const uint64_t* d_off = c.d_off;
+  const uint64_t* d_ids = c.d_ids;
+  const float* d_val = c.d_val;
+  const float* d_lab = c.d_lab;
+  const int push_cnt = c.push_cnt, is_train = c.is_train;
+  cudaEvent_t inputs_ready = c.inputs_ready, consumed = c.consumed;
+  LookupArgs& la = c.la;
   const ShardLayout& lay = sh.lay;
   const int S = sh.S, me = sh.rank, K = h->prm.V_dim;
   const uint64_t t = sh.step;
@@ -70,13 +111,25 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
   void* mine = sh.mailbox;
   const size_t Kseg = lay.Kseg;
 
+  const ShardHdr* hdr[8];
+  for (int r = 0; r < S; ++r) hdr[r] = lay.at<ShardHdr>(mine, lay.off_hdr, lay.str_hdr, d, r);
+  int* flags = sh.flags.as<int>();
+  int* ws = sh.ws.as<int>();
+  const bool auc = c.auc;
+
+  if (phase == 0) {
   // ------------------------------- W part 1: localize, slice, scatter -------------------------------
   if (inputs_ready) DFB_CUDA(h, cudaStreamWaitEvent(W, inputs_ready, 0));
   if (t >= 2) DFB_CUDA(h, cudaStreamWaitEvent(W, sh.ev_fin[d], 0));     // parity slots of step t-2 are free again
   size_t Ucap = 0;
-  DFB_TRY(dfbh::localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, sh.L, W, false, false, &Ucap));   // Localizer(-1), sgd_learner.cc:203
+  if (h->profile && h->prof_steps && h->prof_steps % dfb_engine::kProfRing == 0) DFB_TRY(dfbh::prof_drain(h));
   DFB_TRY(h->ensure(sh.rowcnt, (size_t)S * (nrows + 1) * sizeof(int)));
   DFB_TRY(h->ensure(sh.pred[d], (nrows ? nrows : 1) * sizeof(float)));
+  {
+    StageTimer tm(h, 5, W);
+    DFB_TRY(dfbh::localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, sh.L, W, false, false, &Ucap));   // Localizer(-1), sgd_learner.cc:203
+  }
+  StageTimer tm_slice(h, 6, W);
   ShardBounds* wb = sh.wb.as<ShardBounds>();
   h->launches += launch_shard_bounds(sh.L.keys.as<uint64_t>(), sh.L.dU(), Ucap, sh.L.col_start.as<int>(), nnz, S, Kseg,
                                      lay.Nseg, wb, h->tab.prog, W);
@@ -103,6 +156,7 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
     h->launches += launch_shard_scatter(a, valued, nnz ? nnz : 1, W);
     h->launches += launch_shard_subcsr(d_off, sh.L.lidx.as<uint32_t>(), d_val, nrows, wb, S, sh.rowcnt.as<int>(), rd, fd, W);
   }
+  tm_slice.stop();
   {
     SignalDst sd;
     memset(&sd, 0, sizeof(sd));
@@ -111,25 +165,23 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
     if (remote) h->launches += launch_shard_signal(sd, fv, W);
   }
   DFB_CUDA(h, cudaEventRecord(sh.ev_struct[d], W));
+  }
 
+  if (phase == 1) {
   // ------------------------------- O part 1: lookup, partial interaction sums -------------------------------
   DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_struct[d], 0));
   h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_STRUCT, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, O);
-  LookupArgs la;
+  StageTimer tm_fwd(h, 7, O);
   memset(&la, 0, sizeof(la));
   la.S = S; la.Kseg = Kseg;
   la.stamp = (is_train && S > 1) ? (unsigned)((fv & 0xFFFFFFULL) ? (fv & 0xFFFFFFULL) : 1ULL) : 0u;
   la.slot = sh.slot.as<int>(); la.w = sh.w.as<float>(); la.vrow = sh.vrow.as<int>(); la.wv = sh.wv.as<int2>();
-  const ShardHdr* hdr[8];
   for (int r = 0; r < S; ++r) {
-    hdr[r] = lay.at<ShardHdr>(mine, lay.off_hdr, lay.str_hdr, d, r);
     la.hdr[r] = hdr[r];
     la.keys[r] = lay.at<uint64_t>(mine, lay.off_keys, lay.str_keys, d, r);
   }
   // a validation / prediction batch must not grow the table (a missing entry reads as w = 0, no V)
   h->launches += launch_shard_lookup(h->tab, la, is_train || push_cnt, O);
-  int* flags = sh.flags.as<int>();
-  int* ws = sh.ws.as<int>();
   if (push_cnt) {
     // Push(kFeaCount) before Pull (sgd_learner.cc:214-217): one Update per worker, rank order
     for (int r = 0; r < S; ++r)
@@ -160,6 +212,7 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
     h->launches += nl;
   }
+  tm_fwd.stop();
   {
     SignalDst sd;
     memset(&sd, 0, sizeof(sd));
@@ -168,11 +221,14 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
     if (remote) h->launches += launch_shard_signal(sd, fv, O);
   }
   DFB_CUDA(h, cudaEventRecord(sh.ev_part[d], O));
+  }
 
+  if (phase == 2) {
   // ------------------------------- W part 2: reduce the partials, p and p*XV back -------------------------------
   DFB_CUDA(h, cudaStreamWaitEvent(W, sh.ev_part[d], 0));
   h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_PART, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, W);
   {
+    StageTimer tm_red(h, 8, W);
     ReduceArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.S = S; ra.me = me; ra.train = is_train ? 1 : 0; ra.nrows = nrows;
@@ -195,7 +251,6 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
     if (remote) h->launches += launch_shard_signal(sd, fv, W);
   }
   DFB_CUDA(h, cudaEventRecord(sh.ev_reduce[d], W));
-  const bool auc = h->compute_auc && nrows;
   if (auc) {
     DFB_TRY(h->ensure(h->auc_k, nrows * sizeof(float)));
     DFB_TRY(h->ensure(h->auc_v, nrows * sizeof(float)));
@@ -205,8 +260,11 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
                               h->auc_tmp.p, h->auc_tmp.bytes, &sh.prog_w(d)->auc, A);
     DFB_CUDA(h, cudaEventRecord(sh.ev_auc[d], A));
   }
+  }
 
+  if (phase == 3) {
   // ------------------------------- O part 2: one Update per worker, rank order -------------------------------
+  StageTimer tm_upd(h, 9, O);
   for (int r = 0; r < S; ++r) {
     if (r == me) DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_reduce[d], 0));
     else h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_PXV, r), 8, 1u, fv, sh.timeout_cycles, h->tab.prog, O);
@@ -233,8 +291,11 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
     h->launches += launch_shard_done(sh.src_prog(r), h->tab.prog, lay.at<double>(sh.peer[r], lay.off_pen, lay.str_pen, d, me),
                                      lay.flag(sh.peer[r], ShardLayout::F_DONE, me), fv, O);
   }
+  tm_upd.stop();
   DFB_CUDA(h, cudaEventRecord(sh.ev_upd[d], O));
+  }
 
+  if (phase == 4) {
   // ------------------------------- F: penalties back, Progress snapshot -------------------------------
   DFB_CUDA(h, cudaStreamWaitEvent(F, sh.ev_reduce[d], 0));
   if (auc) DFB_CUDA(h, cudaStreamWaitEvent(F, sh.ev_auc[d], 0));
@@ -250,7 +311,21 @@ int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, c
   DFB_CUDA(h, cudaEventRecord(sh.ev_fin[d], F));
   if (consumed) DFB_CUDA(h, cudaEventRecord(consumed, F));
   sh.step++;
+  c.open = false;
+  if (h->profile) h->prof_steps++;
+  }
   DFB_CUDA(h, cudaGetLastError());
+  return DFB_OK;
+}
+
+int shard_step(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
+               const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready,
+               cudaEvent_t consumed) {
+  DFB_TRY(shard_begin(h, nrows, nnz, d_off, d_ids, d_val, d_lab, push_cnt, is_train, inputs_ready, consumed));
+  for (int ph = 0; ph < 5; ++ph) {
+    int rc = shard_phase(h, ph);
+    if (rc != 0) { h->shard->cx.open = false; return rc; }
+  }
   return DFB_OK;
 }
 
@@ -386,6 +461,30 @@ int dfb_shard_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, con
                       in.lab.as<float>(), push_cnt, is_train, in.copied, in.consumed);
   h->seq++;
   return rc;
+}
+
+int dfb_shard_begin_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids, const float* value,
+                          const float* label, int push_cnt, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_TRY(dfbh::check_csr(h, nrows, offset));
+  if (nrows && !label) return h->fail(DFB_ERR_INVALID, "label is NULL");
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  const size_t nnz = nrows ? (size_t)offset[nrows] : 0;
+  if (nnz && !ids) return h->fail(DFB_ERR_INVALID, "ids is NULL");
+  auto& in = h->in[h->seq & 1];
+  if (!(in.pre_ids == ids && ids && in.pre_nrows == nrows && in.pre_nnz == nnz))
+    DFB_TRY(dfbh::stage_raw(h, in, nrows, nnz, offset, ids, value, label));
+  in.pre_ids = nullptr;
+  int rc = shard_begin(h, nrows, nnz, in.off.as<uint64_t>(), in.ids.as<uint64_t>(), value ? in.val.as<float>() : nullptr,
+                       in.lab.as<float>(), push_cnt, is_train, in.copied, in.consumed);
+  h->seq++;
+  return rc;
+}
+
+int dfb_shard_phase(dfb_handle h, int phase) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  return shard_phase(h, phase);
 }
 
 int dfb_shard_info(dfb_handle h, int* rank, int* nranks, size_t* seg_keys, size_t* seg_nnz, uint64_t* steps) {

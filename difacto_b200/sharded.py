@@ -353,6 +353,90 @@ class FusedShardedStore:
 # ---------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): one process per GPU, launched by torch.distributed.run
 # ---------------------------------------------------------------------------------------------
+def parity_check(rank, world, local_rank, V_dim, steps=4, B=512, nnz_row=24, ids=3000):
+    """Driver-visible multi-GPU parity: a small model is trained (i) by the fused sharded store over all ranks and
+    (ii) on rank 0 by ONE engine through the API-faithful plugin calls a maintainer's difacto would make for the
+    same `world` workers in bulk-synchronous order -- Store::Pull for every worker, FMLoss::Predict / CalcGrad,
+    then Store::Push per worker in rank order (dfb_pull / dfb_predict / dfb_calc_grad / dfb_push_grad).  The
+    entries of every shard are compared with the single engine's (both are the product's CUDA paths; each is
+    separately checked against the oracle by tests/).  Tolerance: state rel 1e-3 / abs 1e-5, flags exact."""
+    from difacto_b200 import capi
+    kw = dict(V_dim=V_dim, l1=0.05, l2=0.01, lr=0.2, V_lr=0.1, V_threshold=1, V_l2=0.01, V_init_scale=0.2, seed=3)
+
+    def batch(r, st):
+        rng = np.random.default_rng(7000 + 100 * r + st)
+        off = (np.arange(B + 1, dtype=np.uint64) * np.uint64(nnz_row))
+        idx = rng.integers(0, ids, B * nnz_row).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        lab = np.where(rng.random(B) < 0.4, 1.0, -1.0).astype(np.float32)
+        return off, idx, lab
+
+    E = capi.Engine(device=local_rank, table_capacity=1 << 16, **kw)
+    store = FusedShardedStore(E, max_rows=B, max_nnz=B * nnz_row)
+    losses = []
+    for st in range(steps):
+        off, idx, lab = batch(rank, st)
+        store.step_host(B, off, idx, None, lab, is_train=True, push_cnt=st == 0)
+        losses.append(E.wait_step().loss)
+    # every key any worker touched; each rank reports the entries it owns
+    E1 = capi.Engine(device=local_rank, table_capacity=1 << 16, **kw) if rank == 0 else None
+    allk = []
+    probe = E1 if E1 is not None else E
+    for st in range(steps):
+        for r in range(world):
+            off, idx, _ = batch(r, st)
+            allk.append(probe.localize(off, idx, want_cnt=False)[1])
+    allk = np.unique(np.concatenate(allk))
+    mine = allk[key_owner_np(allk, world) == rank]
+    scal, hasv, V, cg = E.read_entries(mine)
+    got = [None] * world
+    dist.all_gather_object(got, dict(keys=mine, scal=scal, hasv=hasv, V=V, cg=cg, loss=losses))
+    E.close()
+    if rank != 0:
+        return None
+    # ---- the same training on ONE engine through the plugin-call API ----
+    ref_loss = [[0.0] * steps for _ in range(world)]
+    for st in range(steps):
+        loc = []
+        for r in range(world):
+            off, idx, lab = batch(r, st)
+            lidx, keys, cnt = E1.localize(off, idx)
+            loc.append((off, lidx, lab, keys, cnt))
+        if st == 0:
+            for (_, _, _, keys, cnt) in loc:
+                E1.push_feacnt(keys, cnt)
+        pulled = [E1.pull(keys) for (_, _, _, keys, _) in loc]
+        grads = []
+        for r, (off, lidx, lab, keys, cnt) in enumerate(loc):
+            vals, lens = pulled[r]
+            w_pos = (np.cumsum(lens) - lens).astype(np.int32)
+            V_pos = np.where(lens > 1, w_pos + 1, -1).astype(np.int32)
+            pred = E1.predict(off, lidx, None, vals, w_pos, V_pos)
+            ref_loss[r][st] = E1.evaluate(lab, pred)
+            grads.append(E1.calc_grad(off, lidx, None, lab, vals, pred, w_pos, V_pos))
+        for r, (off, lidx, lab, keys, cnt) in enumerate(loc):
+            E1.push_grad(keys, grads[r], pulled[r][1])
+    worst = dict(w=0.0, V=0.0, cg=0.0)
+    flag_mismatch, fail, n = 0, 0, 0
+    for r in range(world):
+        g = got[r]
+        rs, rh, rV, rcg = E1.read_entries(g["keys"])
+        n += len(g["keys"])
+        flag_mismatch += int((rh != g["hasv"]).sum()) + int((rs[:, 0] != g["scal"][:, 0]).sum())
+        for name, a, b in (("w", g["scal"][:, 1:], rs[:, 1:]), ("V", g["V"], rV), ("cg", g["cg"], rcg)):
+            err = np.abs(a.astype(np.float64) - b)
+            fail += int((err > 1e-5 + 1e-3 * np.abs(b)).sum())
+            worst[name] = max(worst[name], float(err.max()) if err.size else 0.0)
+    loss_rel = max(abs(got[r]["loss"][st] - ref_loss[r][st]) / max(abs(ref_loss[r][st]), 1e-9)
+                   for r in range(world) for st in range(steps))
+    E1.close()
+    return {"checked": True, "what": "fused sharded store over all ranks vs ONE engine driven through dfb_pull / dfb_predict / "
+                                     "dfb_calc_grad / dfb_push_grad for the same workers (rank order), small shape",
+            "shape": {"world": world, "steps": steps, "rows": B, "nnz_per_row": nnz_row, "V_dim": V_dim},
+            "entries_compared": n, "flag_or_count_mismatches": flag_mismatch, "values_out_of_tolerance": fail,
+            "max_abs_err": worst, "max_rel_loss_err": loss_rel, "tolerance": "abs 1e-5 + rel 1e-3 (state), flags exact",
+            "ok": bool(flag_mismatch == 0 and fail == 0 and loss_rel < 1e-4)}
+
+
 def bench_main(args, rank, world, local_rank, benchmod):
     import json
     from difacto_b200 import capi
@@ -363,162 +447,150 @@ def bench_main(args, rank, world, local_rank, benchmod):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     kw = benchmod.hyper(args)
     nb = args.working_set
-    nnz = args.nnz if args.workload == "synthetic" else 39
-    B = args.batch
-    N = B * nnz
+    nnz_row = args.nnz if args.workload == "synthetic" else 39
+    B, k = args.batch, args.vdim
+    N = B * nnz_row
+    steps, warm = args.steps, args.warmup
 
-    # per-rank synthetic batches (data parallel: every rank has its own file part, sgd_learner.cc:78-89)
-    host = []
-    for b in range(nb):
-        off, lab, ids = benchmod.gen_raw_batch(args, 1 + b + 1000 * rank)
-        lidx, keys, cnt = benchmod.localize_np(ids)
-        host.append(dict(nrows=B, nnz=N, U=len(keys), bounds=shard_bounds_np(keys, world),
-                         off=torch.from_numpy(off.view(np.int64)).pin_memory(),
-                         lab=torch.from_numpy(lab).pin_memory(),
-                         lidx=torch.from_numpy(lidx.view(np.int32)).pin_memory(),
-                         keys=torch.from_numpy(keys.view(np.int64)).pin_memory(),
-                         cnt=torch.from_numpy(cnt).pin_memory()))
-    U_mean = float(np.mean([h["U"] for h in host]))
+    # per-rank raw batches in pinned host memory (data parallel: every rank has its own file part, sgd_learner.cc:78-89)
+    host = benchmod.gen_raw_set(args, nb, 1 + 1000 * rank, torch)
+    probe = capi.Engine(device=local_rank, table_capacity=1024, V_dim=k)
+    U0 = len(probe.localize(host[0]["off"].numpy().view(np.uint64), host[0]["ids"].numpy().view(np.uint64), want_cnt=False)[1])
+    probe.close()
     # this shard sees about (all ranks' keys) / world distinct keys
-    cap = int(nb * U_mean * 1.15) + 4096
-    E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap, **kw)
-    backend = CudaBackend(E, dev)
-    use_p2p = os.environ.get("DFB_SHARDED", "p2p") == "p2p" and E.V_dim in (8, 16, 32, 64, 128)
-    store = None
-    if use_p2p:
-        Umax = int(max(h["U"] for h in host) * 1.02) + 1024
-        ok = 1
-        try:
-            store = PeerShardedStore(backend, max_keys=Umax, max_recv_keys=int(Umax * 1.3))
-        except Exception as e:      # e.g. CUDA IPC unavailable: every rank falls back together
-            print(f"[rank {rank}] peer store unavailable ({e!r}); using NCCL all_to_all", flush=True)
-            ok = 0
-        flag = torch.tensor([ok], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        use_p2p = bool(flag.item())
-    if not use_p2p:
-        store = ShardedStore(backend)
-
-    def to_dev(h):
-        d = dict(h)
-        for k in ("off", "lab", "lidx", "keys", "cnt"):
-            d[k] = h[k].to(dev, non_blocking=True)
-        return d
-
-    devb = [to_dev(h) for h in host]
+    cap = int(nb * U0 * 1.15) + 4096
+    id_bits = int(np.ceil(np.log2(float(max(args.id_space, 2))))) if args.workload == "synthetic" else 64
+    extra = dict(kv.split("=") for kv in args.engine_kw.split(",") if kv)
+    E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap, id_bits=min(id_bits, 64), **extra, **kw)
+    # criteo-shaped ids carry the feature group in their low bits, so the reversed keys cluster: full-size segments
+    seg = 0 if args.workload == "synthetic" else N
+    store = FusedShardedStore(E, max_rows=B, max_nnz=N, seg_keys=seg, seg_nnz=seg)
+    devb = [dict(off=h["off"].to(dev), lab=h["lab"].to(dev), ids=h["ids"].to(dev)) for h in host]
     torch.cuda.synchronize()
 
-    with torch.cuda.stream(backend.stream):
-        for p in range(2):      # table warm-up: afterwards every key owns a V row
-            for b in range(nb):
-                store.step(devb[b], True, push_cnt=(p == 0))
-        E.read_progress()
-        for t in range(args.warmup):
-            store.step(devb[t % nb], True)
+    def step_dev(b, push_cnt=False, train=True):
+        d = devb[b]
+        store.step_dev(B, N, d["off"], d["ids"], None, d["lab"], is_train=train, push_cnt=push_cnt)
+
+    for p in range(2):      # table warm-up: afterwards every key has reached its steady state
+        for b in range(nb):
+            step_dev(b, push_cnt=(p == 0))
+    E.read_progress()
+    for t in range(warm):
+        step_dev(t % nb)
+    E.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = E.launch_count()
+    sampler = benchmod.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    wall0 = time.time()
+    E.time_mark(0)
+    for t in range(steps):
+        step_dev((warm + t) % nb)
+    E.time_mark(1)
+    ms = torch.tensor([E.time_elapsed_ms()], device=dev)
+    E.sync()
+    dist.barrier()
+    wall1 = time.time()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = E.launch_count() - launches0
+    prog = E.read_progress()
+
+    # ---- per-phase CUDA-event timings (separate region): their sum exceeds the step time when phases overlap ----
+    E.profile(True)
+    for t in range(max(4, steps // 2)):
+        step_dev((warm + t) % nb)
+    E.sync()
+    st = E.profile_read()
+    E.profile(False)
+    E.read_progress()
+    phases = {n: st[n]["ms"] / max(st[n]["count"], 1) for n in ("localize", "shard_slice_scatter", "shard_owner_partials",
+                                                                "shard_worker_reduce", "shard_owner_updates")}
+    dist.barrier()
+
+    # ---- e2e: raw uint64 CSR from pinned host memory every step + Progress read back ----
+    e2e = None
+    if not args.no_e2e:
+        def run_e2e(nsteps, first):
+            loss = 0.0
+            for t in range(nsteps):
+                h = host[(first + t) % nb]
+                store.step_host(B, h["off"], h["ids"], None, h["lab"], is_train=True)
+                if t + 1 < nsteps:
+                    n_ = host[(first + t + 1) % nb]
+                    E.prefetch_raw(B, n_["off"], n_["ids"], None, n_["lab"])
+                if t >= 1:
+                    loss += E.wait_step().loss      # D2H of step t-1's result while step t runs
+            loss += E.wait_step().loss
+            return loss
+
+        run_e2e(warm, 0)
         E.sync()
         dist.barrier()
         torch.cuda.synchronize()
-        launches0 = E.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = benchmod.ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        wall0 = time.time()
-        ev0.record(backend.stream)
-        for t in range(args.steps):
-            store.step(devb[(args.warmup + t) % nb], True)
-        ev1.record(backend.stream)
+        t0 = time.perf_counter()
+        loss_sum = run_e2e(steps, warm)
         E.sync()
         torch.cuda.synchronize()
         dist.barrier()
-        wall1 = time.time()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item())
-        launches = E.launch_count() - launches0
-        prog = E.read_progress()
-
-        # ---- per-phase CUDA-event timings (separate region) ----
-        store.timers = {}
-        for t in range(max(4, args.steps // 2)):
-            store.step(devb[(args.warmup + t) % nb], True)
-        phases = {k2: v2[0] / max(v2[1], 1) for k2, v2 in store.flush_timers().items()}
-        store.timers = None
-        E.read_progress()
-
-        # ---- e2e: per-step H2D of the localized batch from pinned memory + Progress read back ----
-        e2e = None
-        if not args.no_e2e:
-            # double-buffered input: the H2D copy of batch t+1 runs on a copy stream while step t computes
-            copy_stream = torch.cuda.Stream(device=dev)
-            main = backend.stream
-
-            def prefetch(h):
-                with torch.cuda.stream(copy_stream):
-                    d = to_dev(h)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                return d, ev
-
-            def run_e2e(nsteps, first):
-                loss = 0.0
-                nxt = prefetch(host[first % nb])
-                for t in range(nsteps):
-                    cur, ev = nxt
-                    if t + 1 < nsteps:
-                        nxt = prefetch(host[(first + t + 1) % nb])
-                    main.wait_event(ev)
-                    store.step(cur, True)
-                    for k2 in ("off", "lab", "lidx", "keys", "cnt"):
-                        cur[k2].record_stream(main)
-                    loss += E.read_progress().loss      # D2H of the step's result
-                return loss
-
-            run_e2e(args.warmup, 0)
-            dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            loss_sum = run_e2e(args.steps, args.warmup)
-            torch.cuda.synchronize()
-            dist.barrier()
-            dt = torch.tensor([time.perf_counter() - t0], device=dev)
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            dt = float(dt.item())
-            h2d = (B + 1) * 8 + N * 4 + B * 4 + int(U_mean) * 8
-            e2e = {"value": args.steps * B * world / dt, "unit": "examples/s", "h2d_bytes_per_step": int(h2d),
-                   "d2h_bytes_per_step": 64, "ms_per_step": dt / args.steps * 1e3,
-                   "api": "ShardedStore.step (torch.distributed all_to_all + C-ABI dfb_dev_*), localized CSR + keys "
-                          "from pinned host memory every step"}
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": steps * B * world / dt, "unit": "examples/s", "h2d_bytes_per_step": int((B + 1) * 8 + N * 8 + B * 4),
+               "d2h_bytes_per_step": 64, "ms_per_step": dt / steps * 1e3,
+               "api": "dfb_shard_step_async (+ dfb_prefetch_raw) + dfb_wait_step per rank: raw uint64 CSR from pinned host "
+                      "memory, Localizer::Compact on the GPU, NVLink-sharded fused step; no NCCL call and no host "
+                      "synchronisation inside a step"}
+    st_tab = E.table_stats()
+    loss_all = torch.tensor([prog.loss, prog.nrows], device=dev, dtype=torch.float64)
+    dist.all_reduce(loss_all)
+    E.close()
+    parity = None
+    try:
+        parity = parity_check(rank, world, local_rank, k)
+    except Exception as e:       # the check must never take the number down with it; a failure is reported as such
+        parity = {"checked": False, "error": repr(e)}
     if rank == 0:
         sampler.stop()
-        k = args.vdim
-        a2a_bytes = 2 * U_mean * (world - 1) / world * (8 + 4 * (k + 1))     # BASELINE.md section 3, per direction
+        peak, peak_src = benchmod.load_peaks()
+        fwd, emit, upd, step_model = benchmod.byte_model(B, N, U0, k)
+        # what crosses NVLink per GPU and direction per step: the slices of the batch's structure, the partial sums
+        # ((k+2) floats per row and owner) one way, p and p*XV ((k+1) floats per row and owner) the other way
+        fr = (world - 1) / world
+        nvl_out = fr * (U0 * 12 + N * 8) + (world - 1) * B * (k + 2) * 4 + (world - 1) * B * (k + 1) * 4
+        rows_model = 2 * U0 * fr * (8 + 4 * (k + 1))       # rows of the active keys, pull + push
         nvl = 770.0   # measured peer copy GB/s per direction (B200_PROFILING.md)
+        upd_ms = phases["shard_owner_updates"]
         line = {
-            "metric": benchmod.metric_name(args), "value": args.steps * B * world / (ms * 1e-3), "unit": "examples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "metric": benchmod.metric_name(args), "value": steps * B * world / (ms * 1e-3), "unit": "examples/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": benchmod.workload_config(args, {
-                "unique_keys_per_batch": int(U_mean), "working_set_batches": nb,
-                "parallelism": f"dp{world} minibatches x table sharded by reversed-key range over {world} GPUs "
-                               "(ps-lite rule), Pull/Push of the active rows = "
-                               + ("peer stores over NVLink fused into the gather / gradient kernels (CUDA IPC)"
-                                  if use_p2p else "NCCL all_to_all")}),
-            "roofline": {"bound": "nvlink", "kernel": ("k_gather_rows -> peer pull buffer + k_bwd_update<dense> -> peer push buffer "
-                                                       "(fused compute + NVLink stores)" if use_p2p else
-                                                       "all_to_all of active rows (pull + push)"),
-                         "achieved": a2a_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": nvl, "unit": "GB/s",
-                         "frac": a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / nvl, "traffic": None,
-                         "algorithmic_bytes": int(a2a_bytes),
-                         "note": "bytes that must cross NVLink per GPU per direction per step / whole step time"},
+                "unique_keys_per_batch": int(U0), "working_set_batches": nb, "table_keys_rank0": int(st_tab["n_keys"]),
+                "input": "raw CSR<uint64> per rank, resident in HBM; every step = Localizer::Compact on the GPU + the "
+                         "NVLink-sharded fused minibatch",
+                "parallelism": f"dp{world} minibatches x table sharded by reversed-key range over {world} GPUs (ps-lite rule); "
+                               "owners compute the partial FM interaction sums of every worker's rows (k+2 floats per row "
+                               "cross NVLink instead of k floats per key), per-key gradient + FTRL/AdaGrad on the owner; "
+                               "peer stores + step-counter flags in peer memory (CUDA IPC), no NCCL in the step"}),
+            "roofline": {"bound": "hbm", "kernel": f"k_bwd_update<{k},shard> x {world} workers (owner-side per-key gradient "
+                                                   "reduce + FTRL/AdaGrad; the timed phase includes waiting for the workers' p*XV)",
+                         "achieved": upd / (upd_ms * 1e-3) / 1e9 if upd_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                         "frac": upd / (upd_ms * 1e-3) / 1e9 / peak if upd_ms > 0 else 0.0, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": upd_ms, "algorithmic_bytes": int(upd),
+                         "nvlink": {"bytes_out_per_gpu_per_step": int(nvl_out),
+                                    "achieved_GBps_over_whole_step": nvl_out / (ms / steps * 1e-3) / 1e9, "peak_GBps": nvl,
+                                    "rows_exchange_model_bytes": int(rows_model),
+                                    "note": "the step is HBM-bound again: the rows stay on their owner; the row-exchange "
+                                            "protocol of round 1 would move rows_exchange_model_bytes per direction"}},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(wall0, wall1), "loss_per_example": prog.loss / max(prog.nrows, 1),
-            "phases_ms_per_step_rank0": phases,
+            "clocks": sampler.summary(wall0, wall1), "loss_per_example": float(loss_all[0] / max(loss_all[1], 1)),
+            "phases_ms_per_step_rank0": phases, "phases_sum_ms": float(sum(phases.values())), "parity": parity,
         }
         print(json.dumps(line), flush=True)
-    # Tensors (device and pinned host) that were used on the engine's stream record events on it
-    # when they are freed, which at interpreter teardown can happen after the stream is gone:
-    # finish cleanly and leave without running destructors.
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()

@@ -212,13 +212,20 @@ int dfb_train_step_raw_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_
  * beyond that the oldest snapshots are folded into the sum dfb_read_progress returns. */
 int dfb_wait_step(dfb_handle h, dfb_progress* out);
 
-/* per-stage device timing with CUDA events on the handle's stream (bench.py's roofline):
+/* per-stage device timing with CUDA events on the stream each stage runs on (bench.py's roofline):
  * stage 0 = key lookup + pull, 1 = FM forward kernel, 2 = AUC, 3 = CSC sort of the batch,
- * 4 = per-key gradient reduce + FTRL/AdaGrad update (+ InitV pass).
+ * 4 = per-key gradient reduce + FTRL/AdaGrad update (+ InitV pass), 5 = GPU localizer (raw batches);
+ * sharded store: 6 = worker: slice the batch + scatter to the owners, 7 = owner: lookup + partial interaction
+ * sums of all workers' rows, 8 = worker: reduce the partials (pred / loss / p, p*XV back), 9 = owner: the
+ * workers' updates (incl. waiting for their p*XV).
  * dfb_profile_read returns the accumulated milliseconds and launch counts of the DFB_NUM_STAGES
  * stages and resets them.  While profiling, AUC runs on the main stream (otherwise it overlaps
- * the update on an auxiliary stream). */
-#define DFB_NUM_STAGES 5
+ * the update on an auxiliary stream).
+ * dfb_time_mark(h, 0) / (h, 1) bracket a region with CUDA events that cover ALL streams of the handle
+ * (mark 1 joins them); dfb_time_elapsed_ms synchronises and returns the device time between the marks. */
+#define DFB_NUM_STAGES 10
+int dfb_time_mark(dfb_handle h, int which);
+int dfb_time_elapsed_ms(dfb_handle h, float* ms);
 int dfb_profile(dfb_handle h, int enable);
 int dfb_profile_read(dfb_handle h, double* stage_ms, uint64_t* stage_count);
 
@@ -325,6 +332,15 @@ int dfb_shard_step_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d
                        const float* d_value_or_null, const float* d_label, int push_cnt, int is_train);
 int dfb_shard_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
                          const float* value_or_null, const float* label, int push_cnt, int is_train);
+/* The same step split into its five enqueue phases (0 worker: localize + scatter the slices, 1 owner: lookup +
+ * partial sums, 2 worker: reduce + p*XV back, 3 owner: updates, 4 finish): dfb_shard_step_* is begin + phases
+ * 0..4.  Needed only when ONE host thread drives several engines that share ONE device (tests): there the
+ * phases must be interleaved -- phase p of every engine before phase p+1 of any -- so that every device-side
+ * wait refers to work that is already enqueued.  Engines on different devices (or driven by different
+ * threads / processes) just call dfb_shard_step_*. */
+int dfb_shard_begin_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
+                          const float* value_or_null, const float* label, int push_cnt, int is_train);
+int dfb_shard_phase(dfb_handle h, int phase);
 int dfb_shard_info(dfb_handle h, int* rank, int* nranks, size_t* seg_keys, size_t* seg_nnz, uint64_t* steps);
 
 /* the CUDA stream (cudaStream_t) the handle enqueues on, for event interop with torch */
