@@ -28,6 +28,9 @@ def build(ref=True, quiet=True):
     subprocess.check_call(["make", "-C", HERE, "all"], stdout=out)
     if ref and os.path.isdir(os.environ.get("DIFACTO_REF", "/root/reference")):
         subprocess.check_call(["make", "-C", HERE, "ref", "-j8"], stdout=out)
+        # the reference's own SGDLearner linked with the GPU plugins of ../integration (the drop-in proof; a test target)
+        if os.path.exists(os.path.join(HERE, "..", "difacto_b200", "lib", "libdifacto_b200.so")):
+            subprocess.check_call(["make", "-C", HERE, "ref_gpu", "-j8"], stdout=out)
 
 
 def have_ref():

@@ -77,6 +77,14 @@ def main():
                                batch_size=100, max_num_epochs=20, stop_rel_objv=0)
     out["sgd_v0_trace"] = tr
 
+    # --- the reference's own SGDLearner with V_dim > 0 and a validation set (unpinned by reference tests): the
+    #     trace the GPU-plugged learner of integration/ must reproduce (tests/test_gpu_reference_binding.py) ---
+    kwl = dict(data_in=REF_DATA, data_val=REF_DATA, V_dim=8, l1=0.05, l2=0.01, lr=0.1, V_lr=0.05, V_threshold=1,
+               V_l2=0.01, V_init_scale=0.1, seed=3, num_jobs_per_epoch=1, batch_size=100, max_num_epochs=12,
+               stop_rel_objv=0, stop_val_auc=-1e9)
+    out["sgd_v8_learner_kwargs"] = np.array([f"{a}={b}" for a, b in kwl.items() if a not in ("data_in", "data_val")])
+    out["sgd_v8_learner_trace"] = O.ref_sgd_learner_run(**kwl)
+
     # --- V_dim>0 SGD on the fixture through the reference step (unpinned by reference tests) ---
     kw = dict(V_dim=8, l1=0.05, l2=0.01, lr=0.1, V_lr=0.05, V_threshold=1, V_l2=0.01,
               V_init_scale=0.1, seed=3)
