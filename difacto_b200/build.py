@@ -63,5 +63,29 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, extra_flags):
+    """a tuning build with extra nvcc flags -> lib/variants/<name>.so (load it with DFB_LIB=...; never the product)"""
+    vdir = os.path.join(LIBDIR, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [NVCC] + [f for f in FLAGS if f not in ("-Xptxas", "-v")] + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out = p.communicate()[0]
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src}")
+    lib = os.path.join(LIBDIR, "variants", name + ".so")
+    subprocess.check_call([NVCC, "-shared", "-o", lib] + objs + ["-cudart", "static", "-ccbin",
+                                                                 "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"])
+    for o in objs:
+        os.remove(o)
+    return lib
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

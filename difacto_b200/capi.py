@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libdifacto_b200.so")
+LIB_PATH = os.environ.get("DFB_LIB") or os.path.join(HERE, "lib", "libdifacto_b200.so")   # DFB_LIB: a tuning build
 
 DFB_OK, DFB_ERR_INVALID, DFB_ERR_CUDA, DFB_ERR_CAPACITY, DFB_ERR_PARAM = 0, -1, -2, -3, -4
 

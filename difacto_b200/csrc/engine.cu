@@ -433,7 +433,8 @@ int step_raw_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off,
                  const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready,
                  bool exact_range = false) {
   dfb_engine::LocSet& L = h->loc[h->loc_seq & 1];
-  cudaStream_t ls = h->loc_stream;
+  // while profiling the localizer shares the main stream: per-stage times are then those of kernels running alone
+  cudaStream_t ls = h->profile ? h->stream : h->loc_stream;
   if (inputs_ready) DFB_CUDA(h, cudaStreamWaitEvent(ls, inputs_ready, 0));
   if (L.used) DFB_CUDA(h, cudaStreamWaitEvent(ls, L.consumed, 0));
   const bool dev_count_ok = !h->force_generic && fm_fast_supported(h->prm.V_dim) && (!is_train || h->scatter_sorted);

@@ -107,12 +107,16 @@ __device__ __forceinline__ void block_add_loss(float loss_acc, size_t nrows, Dev
 #ifndef DFB_FM_MINBLOCKS
 #define DFB_FM_MINBLOCKS 4
 #endif
+#ifndef DFB_FM_PF_MAXK
+#define DFB_FM_PF_MAXK 16       // metadata prefetch (one chunk ahead) for V_dim <= this
+#endif
 template <int K, int MODE, bool HAS_VAL>
 __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, FmView v, PartArgs pa) {
   constexpr bool TRAIN = MODE == 1;
   constexpr int LPR = K / 4;                 // lanes per V row, one float4 each
   constexpr int G = 32 / LPR;                // V rows fetched by one warp-wide load
   constexpr int UNR = (32 / G) < 8 ? (32 / G) : 8;   // independent loads in flight per lane
+  constexpr bool PF = K <= DFB_FM_PF_MAXK;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR, grp = lane / LPR;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -140,14 +144,13 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     float acc2 = 0.f, wsum = 0.f;
 
-    for (uint64_t c = o0; c < o1; c += 32) {
+    // the per-nnz metadata {x, w, V-row index} of a 32-nnz chunk hangs on a dependent chain (index -> pulled view);
+    // it is fetched one chunk ahead, so that chain overlaps the V-row gathers of the current chunk
+    auto load_meta = [&](uint64_t c, float& x, float& w, int& vr) {
       const uint64_t j = c + lane;
-      const bool valid = j < o1;
-      uint32_t u = 0;
-      float x = 0.f, w = 0.f;
-      int vr = -1;
-      if (valid) {
-        u = __ldg(idxp + j);
+      x = 0.f; w = 0.f; vr = -1;
+      if (j < o1) {
+        const uint32_t u = __ldg(idxp + j);
         x = HAS_VAL ? __ldg(valp + j) : 1.f;
         if (wvp) {
           const int2 t = ldg64_pol(wvp + u, pol_wv);
@@ -163,6 +166,19 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
           if (HAS_VAL) b.occ_rowx[j] = ((unsigned long long)row << 32) | (unsigned long long)__float_as_uint(x);
           else b.occ_row[j] = (uint32_t)row;
         }
+      }
+    };
+    float x_n = 0.f, w_n = 0.f;
+    int vr_n = -1;
+    if (PF) load_meta(o0, x_n, w_n, vr_n);
+    for (uint64_t c = o0; c < o1; c += 32) {
+      float x, w;
+      int vr;
+      if (PF) {
+        x = x_n; w = w_n; vr = vr_n;
+        if (c + 32 < o1) load_meta(c + 32, x_n, w_n, vr_n);
+      } else {
+        load_meta(c, x, w, vr);
       }
       wsum = fmaf(x, w, wsum);
       const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);

@@ -313,70 +313,96 @@ __global__ void __launch_bounds__(256) k_shard_reduce(ReduceArgs a) {
 // ------------------------------------------------------------------------------------------------------
 // owner side
 // ------------------------------------------------------------------------------------------------------
-// model_[key] for the key segments of all workers in one launch (SGDUpdater::Get, sgd_updater.cc:32-56),
-// virtual index v = worker * Kseg + i.  With stamp != 0 every touched entry also records which workers
-// hold it in this step (entry.pad = stamp << 8 | worker bitmask): a key shared by several workers is updated
-// once per worker in rank order, and the later ones need its pull-time V (k_shard_conflicts).
+// model_[key] for the key segment ONE worker sent (SGDUpdater::Get, sgd_updater.cc:32-56); the owner runs it once
+// per worker, in rank order.  With stamp != 0 every touched entry also records which workers hold it in this
+// step (entry.pad = stamp << 8 | worker bitmask).  A key that a lower-rank worker also holds will already have
+// been updated by that worker's push when this worker's push is applied, but the gradient a worker pushes is
+// taken at the V it pulled (fm_loss.h:181-188): such keys are flagged (conf) and their pull-time V row is saved
+// here, while the entry is at hand (warp-cooperative copy).
 template <bool INSERT>
-__global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a) {
+__global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a, int r, unsigned char* __restrict__ conf,
+                                                      float* __restrict__ vsave, int K) {
   constexpr int ILP = 2;
-  const size_t total = (size_t)a.S * a.Kseg;
+  const size_t n = (size_t)a.hdr[r]->nkeys < a.Kseg ? (size_t)a.hdr[r]->nkeys : a.Kseg;
+  const uint64_t* __restrict__ keys = a.keys[r];
+  const size_t o = (size_t)r * a.Kseg;
+  const int lane = threadIdx.x & 31;
   const size_t tile = (size_t)blockDim.x * ILP;
-  for (size_t base = (size_t)blockIdx.x * tile; base < total; base += (size_t)gridDim.x * tile) {
+  const size_t npad = (n + tile - 1) / tile * tile;
+  for (size_t base = (size_t)blockIdx.x * tile; base < npad; base += (size_t)gridDim.x * tile) {
     unsigned long long key[ILP];
     uint64_t h[ILP];
     Entry256 e[ILP];
-    bool valid[ILP];
+    int vr_q[ILP], cf_q[ILP];
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
-      const size_t v = base + (size_t)q * blockDim.x + threadIdx.x;
-      const int r = (int)(v / a.Kseg);
-      const size_t i = v - (size_t)r * a.Kseg;
-      valid[q] = v < total && i < (size_t)a.hdr[r]->nkeys;
-      key[q] = valid[q] ? a.keys[r][i] : 0ULL;
+      const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
+      key[q] = i < n ? keys[i] : 0ULL;
       h[q] = hash64(key[q]) & t.mask;
     }
 #pragma unroll
-    for (int q = 0; q < ILP; ++q)
-      if (valid[q]) e[q] = load_entry(&t.tab[h[q]]);
+    for (int q = 0; q < ILP; ++q) {
+      const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
+      if (i < n) e[q] = load_entry(&t.tab[h[q]]);
+    }
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
-      if (!valid[q]) continue;
-      const size_t v = base + (size_t)q * blockDim.x + threadIdx.x;
+      const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
+      vr_q[q] = -1; cf_q[q] = 0;
+      if (i >= n) continue;
       int slot = -1, vr = -1;
       float w = 0.f;
       if (key[q] == kEmptyKey) {
         raise_err(t.prog, DFB_ERR_INVALID);
+      } else if (e[q].key == key[q]) {
+        slot = (int)h[q]; w = e[q].w(); vr = e[q].vrow();
       } else {
-        if (e[q].key == key[q]) {
-          slot = (int)h[q]; w = e[q].w(); vr = e[q].vrow();
-        } else {
-          slot = table_find<INSERT>(t, key[q], h[q]);
-          if (slot >= 0) { w = t.tab[slot].w; vr = t.tab[slot].vrow; }
-        }
+        slot = table_find<INSERT>(t, key[q], h[q]);
+        if (slot >= 0) { w = t.tab[slot].w; vr = t.tab[slot].vrow; }
       }
+      const size_t v = o + i;
       a.slot[v] = slot;
       a.w[v] = w;
       a.vrow[v] = vr;
       a.wv[v] = make_int2(__float_as_int(w), vr);
-      if (a.stamp != 0 && slot >= 0) {
-        const int r = (int)(v / a.Kseg);
-        int* pad = &t.tab[slot].pad;
-        int old = *reinterpret_cast<volatile int*>(pad);
-        for (;;) {
-          const int fresh = ((((unsigned)old) >> 8) == a.stamp ? old : (int)(a.stamp << 8)) | (1 << r);
-          const int prev = atomicCAS(pad, old, fresh);
-          if (prev == old) break;
-          old = prev;
+      if (a.stamp != 0) {
+        int c = 0;
+        if (slot >= 0) {
+          int* pad = &t.tab[slot].pad;
+          int old = *reinterpret_cast<volatile int*>(pad);
+          for (;;) {
+            const bool cur = (((unsigned)old) >> 8) == a.stamp;
+            const int fresh = (cur ? old : (int)(a.stamp << 8)) | (1 << r);
+            const int prev = atomicCAS(pad, old, fresh);
+            if (prev == old) { c = (cur && (old & ((1 << r) - 1) & 0xff) != 0) ? 1 : 0; break; }
+            old = prev;
+          }
+        }
+        conf[v] = (unsigned char)c;
+        cf_q[q] = c; vr_q[q] = vr;
+      }
+    }
+    if (a.stamp != 0) {
+#pragma unroll
+      for (int q = 0; q < ILP; ++q) {
+        unsigned m = __ballot_sync(kFullMask, cf_q[q] != 0 && vr_q[q] >= 0);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int vrb = __shfl_sync(kFullMask, vr_q[q], b);
+          const size_t ib = base + (size_t)q * blockDim.x + (threadIdx.x - lane) + b;
+          const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vrb * t.rs);
+          float4* dst = reinterpret_cast<float4*>(vsave + (o + ib) * (size_t)K);
+          for (int l = lane; l < K / 4; l += 32) dst[l] = src[l];
         }
       }
     }
   }
 }
 
-// conf[v] = a lower-rank worker holds the same key in this step; such keys get their pull-time V row saved
-// (the gradient a worker pushes is taken at the V it pulled, fm_loss.h:181-188)
-__global__ void __launch_bounds__(256) k_shard_conflicts(Table t, LookupArgs a, unsigned char* __restrict__ conf,
+// feature-count steps: Update(kFeaCount) may allocate V rows between the lookup and the Pull, so the pull-time rows
+// of the flagged keys are saved again from the refreshed view
+__global__ void __launch_bounds__(256) k_shard_save_conf(Table t, LookupArgs a, const unsigned char* __restrict__ conf,
                                                          float* __restrict__ vsave, int K) {
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -384,18 +410,13 @@ __global__ void __launch_bounds__(256) k_shard_conflicts(Table t, LookupArgs a, 
   const size_t total = (size_t)a.S * a.Kseg;
   for (size_t base = warp0 * 32; base < total; base += nwarps * 32) {
     const size_t v = base + lane;
-    const int r = (int)(v / a.Kseg);
-    const size_t i = v - (size_t)r * a.Kseg;
-    int c = 0, vr = -1;
-    if (v < total && i < (size_t)a.hdr[r]->nkeys) {
-      const int s = a.slot[v];
-      if (s >= 0) {
-        const unsigned pad = (unsigned)t.tab[s].pad;
-        if ((pad >> 8) == a.stamp && (pad & ((1u << r) - 1u) & 0xffu) != 0u) { c = 1; vr = a.vrow[v]; }
-      }
-      conf[v] = (unsigned char)c;
+    int vr = -1;
+    if (v < total) {
+      const int r = (int)(v / a.Kseg);
+      const size_t i = v - (size_t)r * a.Kseg;
+      if (i < (size_t)a.hdr[r]->nkeys && conf[v]) vr = a.vrow[v];
     }
-    unsigned m = __ballot_sync(kFullMask, c != 0 && vr >= 0);
+    unsigned m = __ballot_sync(kFullMask, vr >= 0);
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
@@ -504,18 +525,17 @@ int launch_shard_reduce(int V_dim, const ReduceArgs& a, cudaStream_t s) {
   return -1;
 }
 
-int launch_shard_lookup(Table& t, const LookupArgs& a, bool insert, cudaStream_t s) {
-  const size_t total = (size_t)a.S * a.Kseg;
-  const int grid = grid_cap(total, 256 * 2, 148 * 64);
-  if (insert) k_shard_lookup<true><<<grid, 256, 0, s>>>(t, a);
-  else        k_shard_lookup<false><<<grid, 256, 0, s>>>(t, a);
+int launch_shard_lookup(Table& t, const LookupArgs& a, int r, bool insert, unsigned char* conf, float* vsave, int K,
+                        cudaStream_t s) {
+  const int grid = grid_cap(a.Kseg, 256 * 2, 148 * 64);
+  if (insert) k_shard_lookup<true><<<grid, 256, 0, s>>>(t, a, r, conf, vsave, K);
+  else        k_shard_lookup<false><<<grid, 256, 0, s>>>(t, a, r, conf, vsave, K);
   return 1;
 }
 
-int launch_shard_conflicts(Table& t, const LookupArgs& a, unsigned char* conf, float* vsave, int K,
-                           cudaStream_t s) {
+int launch_shard_save_conf(Table& t, const LookupArgs& a, const unsigned char* conf, float* vsave, int K, cudaStream_t s) {
   const size_t total = (size_t)a.S * a.Kseg;
-  k_shard_conflicts<<<grid_cap((total + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, a, conf, vsave, K);
+  k_shard_save_conf<<<grid_cap((total + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, a, conf, vsave, K);
   return 1;
 }
 

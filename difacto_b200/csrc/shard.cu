@@ -181,7 +181,9 @@ int shard_phase(dfb_engine* h, int phase) {
     la.keys[r] = lay.at<uint64_t>(mine, lay.off_keys, lay.str_keys, d, r);
   }
   // a validation / prediction batch must not grow the table (a missing entry reads as w = 0, no V)
-  h->launches += launch_shard_lookup(h->tab, la, is_train || push_cnt, O);
+  for (int r = 0; r < S; ++r)
+    h->launches += launch_shard_lookup(h->tab, la, r, is_train || push_cnt, sh.conf.as<unsigned char>(),
+                                       sh.vsave.as<float>(), K, O);
   if (push_cnt) {
     // Push(kFeaCount) before Pull (sgd_learner.cc:214-217): one Update per worker, rank order
     for (int r = 0; r < S; ++r)
@@ -190,8 +192,8 @@ int shard_phase(dfb_engine* h, int phase) {
     for (int r = 0; r < S; ++r)
       h->launches += launch_pull_view(h->tab, la.slot + (size_t)r * Kseg, Kseg, &hdr[r]->nkeys, la.w + (size_t)r * Kseg,
                                       la.vrow + (size_t)r * Kseg, la.wv + (size_t)r * Kseg, O);
+    if (la.stamp) h->launches += launch_shard_save_conf(h->tab, la, sh.conf.as<unsigned char>(), sh.vsave.as<float>(), K, O);
   }
-  if (la.stamp) h->launches += launch_shard_conflicts(h->tab, la, sh.conf.as<unsigned char>(), sh.vsave.as<float>(), K, O);
   {
     PartArgs pa;
     memset(&pa, 0, sizeof(pa));

@@ -355,11 +355,12 @@ class FusedShardedStore:
 # ---------------------------------------------------------------------------------------------
 def parity_check(rank, world, local_rank, V_dim, steps=4, B=512, nnz_row=24, ids=3000):
     """Driver-visible multi-GPU parity: a small model is trained (i) by the fused sharded store over all ranks and
-    (ii) on rank 0 by ONE engine through the API-faithful plugin calls a maintainer's difacto would make for the
-    same `world` workers in bulk-synchronous order -- Store::Pull for every worker, FMLoss::Predict / CalcGrad,
-    then Store::Push per worker in rank order (dfb_pull / dfb_predict / dfb_calc_grad / dfb_push_grad).  The
-    entries of every shard are compared with the single engine's (both are the product's CUDA paths; each is
-    separately checked against the oracle by tests/).  Tolerance: state rel 1e-3 / abs 1e-5, flags exact."""
+    (ii) on rank 0 through the API-faithful plugin calls a maintainer's difacto would make for the same `world`
+    workers and `world` servers in bulk-synchronous order -- Store::Pull for every worker (keys sliced per server),
+    FMLoss::Predict / CalcGrad, then Store::Push per worker in rank order (dfb_pull / dfb_predict / dfb_calc_grad /
+    dfb_push_grad).  The entries of every shard are compared with the corresponding server engine's (both are the
+    product's CUDA paths; each is separately checked against the oracle by tests/).  Tolerance: state rel 1e-3 /
+    abs 1e-5, flags exact."""
     from difacto_b200 import capi
     kw = dict(V_dim=V_dim, l1=0.05, l2=0.01, lr=0.2, V_lr=0.1, V_threshold=1, V_l2=0.01, V_init_scale=0.2, seed=3)
 
@@ -393,44 +394,64 @@ def parity_check(rank, world, local_rank, V_dim, steps=4, B=512, nnz_row=24, ids
     E.close()
     if rank != 0:
         return None
-    # ---- the same training on ONE engine through the plugin-call API ----
+    # ---- the same training through the plugin-call API: `world` server engines (all on this GPU), `world` workers ----
+    E1.close()
+    srv = [capi.Engine(device=local_rank, table_capacity=1 << 16, **kw) for _ in range(world)]   # same seed per server, as above
+    F = srv[0]      # any engine serves the stateless calls (localize / predict / calc_grad / evaluate)
     ref_loss = [[0.0] * steps for _ in range(world)]
     for st in range(steps):
         loc = []
         for r in range(world):
             off, idx, lab = batch(r, st)
-            lidx, keys, cnt = E1.localize(off, idx)
-            loc.append((off, lidx, lab, keys, cnt))
-        if st == 0:
-            for (_, _, _, keys, cnt) in loc:
-                E1.push_feacnt(keys, cnt)
-        pulled = [E1.pull(keys) for (_, _, _, keys, _) in loc]
+            lidx, keys, cnt = F.localize(off, idx)
+            own = key_owner_np(keys, world)
+            loc.append((off, lidx, lab, keys, cnt, [np.nonzero(own == s_)[0] for s_ in range(world)]))
+        if st == 0:     # Push(kFeaCount): one Update per worker on every server, rank order (sgd_learner.cc:214-217)
+            for s_ in range(world):
+                for (_, _, _, keys, cnt, seg) in loc:
+                    if len(seg[s_]):
+                        srv[s_].push_feacnt(keys[seg[s_]], cnt[seg[s_]])
+        pulled = []
+        for (_, _, _, keys, _, seg) in loc:     # Store::Pull: the sorted key list sliced per server (kv_app.h:416-429)
+            parts = [srv[s_].pull(keys[seg[s_]]) if len(seg[s_]) else (np.zeros(0, np.float32), np.zeros(0, np.int32))
+                     for s_ in range(world)]
+            pulled.append((np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])))
         grads = []
-        for r, (off, lidx, lab, keys, cnt) in enumerate(loc):
+        for r, (off, lidx, lab, keys, cnt, seg) in enumerate(loc):
             vals, lens = pulled[r]
             w_pos = (np.cumsum(lens) - lens).astype(np.int32)
             V_pos = np.where(lens > 1, w_pos + 1, -1).astype(np.int32)
-            pred = E1.predict(off, lidx, None, vals, w_pos, V_pos)
-            ref_loss[r][st] = E1.evaluate(lab, pred)
-            grads.append(E1.calc_grad(off, lidx, None, lab, vals, pred, w_pos, V_pos))
-        for r, (off, lidx, lab, keys, cnt) in enumerate(loc):
-            E1.push_grad(keys, grads[r], pulled[r][1])
+            pred = F.predict(off, lidx, None, vals, w_pos, V_pos)
+            ref_loss[r][st] = F.evaluate(lab, pred)
+            grads.append((F.calc_grad(off, lidx, None, lab, vals, pred, w_pos, V_pos), w_pos))
+        for s_ in range(world):                  # Store::Push(kGradient): one Update per worker, rank order
+            for r, (off, lidx, lab, keys, cnt, seg) in enumerate(loc):
+                ix = seg[s_]
+                if not len(ix):
+                    continue
+                lens = pulled[r][1]
+                g, w_pos = grads[r]
+                lo, hi = int(w_pos[ix[0]]), int(w_pos[ix[-1]] + lens[ix[-1]])
+                srv[s_].push_grad(keys[ix], g[lo:hi], lens[ix])
     worst = dict(w=0.0, V=0.0, cg=0.0)
     flag_mismatch, fail, n = 0, 0, 0
     for r in range(world):
         g = got[r]
-        rs, rh, rV, rcg = E1.read_entries(g["keys"])
+        rs, rh, rV, rcg = srv[r].read_entries(g["keys"])
         n += len(g["keys"])
         flag_mismatch += int((rh != g["hasv"]).sum()) + int((rs[:, 0] != g["scal"][:, 0]).sum())
-        for name, a, b in (("w", g["scal"][:, 1:], rs[:, 1:]), ("V", g["V"], rV), ("cg", g["cg"], rcg)):
-            err = np.abs(a.astype(np.float64) - b)
-            fail += int((err > 1e-5 + 1e-3 * np.abs(b)).sum())
+        for name, a_, b_ in (("w", g["scal"][:, 1:], rs[:, 1:]), ("V", g["V"], rV), ("cg", g["cg"], rcg)):
+            err = np.abs(a_.astype(np.float64) - b_)
+            fail += int((err > 1e-5 + 1e-3 * np.abs(b_)).sum())
             worst[name] = max(worst[name], float(err.max()) if err.size else 0.0)
     loss_rel = max(abs(got[r]["loss"][st] - ref_loss[r][st]) / max(abs(ref_loss[r][st]), 1e-9)
                    for r in range(world) for st in range(steps))
-    E1.close()
-    return {"checked": True, "what": "fused sharded store over all ranks vs ONE engine driven through dfb_pull / dfb_predict / "
-                                     "dfb_calc_grad / dfb_push_grad for the same workers (rank order), small shape",
+    for e_ in srv:
+        e_.close()
+    return {"checked": True, "what": "fused sharded store over all ranks vs the reference's dataflow through the plugin calls: `world` "
+                                     "server engines + `world` workers on rank 0's GPU, Store::Pull (dfb_pull, keys sliced per "
+                                     "server) -> dfb_predict / dfb_calc_grad -> Store::Push (dfb_push_grad) per worker in rank "
+                                     "order; small shape",
             "shape": {"world": world, "steps": steps, "rows": B, "nnz_per_row": nnz_row, "V_dim": V_dim},
             "entries_compared": n, "flag_or_count_mismatches": flag_mismatch, "values_out_of_tolerance": fail,
             "max_abs_err": worst, "max_rel_loss_err": loss_rel, "tolerance": "abs 1e-5 + rel 1e-3 (state), flags exact",
