@@ -103,6 +103,19 @@ struct ShardApply {
   const float* vsave;           // ... and this is its V row as pulled at step start ([n][K])
 };
 
+// very hot keys (a Criteo feature that occurs in most rows of a batch): their occurrence lists are cut into chunks
+// that are reduced by separate warps beforehand (k_hot_reduce), in a fixed order, so that no single warp walks a
+// 65536-row list; k_bwd_update then adds the chunk partials in chunk order (bit-reproducible)
+struct HotPart {
+  const int* hotmap;        // per key: first chunk id (only valid for keys longer than `split`), < 0: not pre-reduced
+  const float* part;        // [chunks][K] partial sum_occ x * pXV[row]
+  const float2* part_s;     // [chunks] partial {sum x p, sum x^2 p}
+  int split, chunk;         // lists longer than split are cut into chunks of `chunk` occurrences; part == nullptr: off
+};
+struct HotWs {              // device workspaces of the pre-reduction
+  int* hotmap; int2* info; float* part; float2* part_s; unsigned long long* counter; int cap;
+};
+
 // forward "partials" of the fused sharded store (MODE 3 of k_fm_fast): the owner of a key segment computes,
 // for every row of every worker's minibatch, the part of the FM interaction that is linear in ITS rows
 //   XV_i^(s) = sum_{j in segment s} x_ij V_j,  sum_j (x_ij V_j)^2,  sum_j x_ij w_j
@@ -245,7 +258,11 @@ int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t 
 int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,
                       const unsigned long long* dn, const int* col_start, const int* col_end,
                       const void* occ_sorted, bool valued, const float* p_row, const float* pxv, int* flags,
-                      int accumulate_penalty, const ShardApply* shard, cudaStream_t s);
+                      int accumulate_penalty, const ShardApply* shard, const HotPart* hot, cudaStream_t s);
+// pre-reduction of the very hot keys' occurrence lists (split > 0); fills *hp for launch_bwd_update
+int launch_hot_prereduce(int V_dim, size_t n, const unsigned long long* dn, const int* col_start, const int* col_end,
+                         const void* occ_sorted, bool valued, const float* p_row, const float* pxv, int split,
+                         const HotWs& ws, HotPart* hp, cudaStream_t s);
 int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_pulled,
                      const int* hasv, size_t n, const int* col_start, const int* col_end,
                      const void* occ_sorted, bool valued, const float* p_row, const float* pxv,

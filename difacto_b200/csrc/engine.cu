@@ -130,6 +130,22 @@ int dfbh::ensure_key_ws(dfb_engine* h, size_t n) {
   return 0;
 }
 using dfbh::ensure_key_ws;
+
+int dfbh::hot_ws(dfb_engine* h, size_t nkeys, size_t nnz, HotWs* ws) {
+  memset(ws, 0, sizeof(*ws));
+  if (h->hot_split <= 0) return 0;
+  const size_t chunk = h->hot_split / 2 > 32 ? h->hot_split / 2 : 32;
+  const size_t cap = nnz / chunk + nnz / (size_t)h->hot_split + 64;
+  DFB_TRY(h->ensure(h->hot_map, (nkeys ? nkeys : 1) * sizeof(int)));
+  DFB_TRY(h->ensure(h->hot_info, cap * sizeof(int2)));
+  DFB_TRY(h->ensure(h->hot_part, cap * (size_t)h->tab.ks * sizeof(float)));
+  DFB_TRY(h->ensure(h->hot_ps, cap * sizeof(float2)));
+  DFB_TRY(h->ensure(h->hot_cnt, 16));
+  ws->hotmap = h->hot_map.as<int>(); ws->info = h->hot_info.as<int2>(); ws->part = h->hot_part.as<float>();
+  ws->part_s = h->hot_ps.as<float2>(); ws->counter = h->hot_cnt.as<unsigned long long>(); ws->cap = (int)cap;
+  return 0;
+}
+
 namespace {
 
 int h2d(dfb_engine* h, DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
@@ -295,11 +311,16 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   }
   StageTimer tm_upd(h, 4);
   if (sorted) {
-    int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U, dU,
-                               csc ? csc->col_start.as<int>() : h->col_start.as<int>(),
-                               csc ? csc->col_end.as<int>() : h->col_end.as<int>(),
-                               csc ? csc->occ_sorted.p : h->occ_sorted.p, d_val != nullptr, h->p_row.as<float>(),
-                               h->pxv.as<float>(), flags, 1, nullptr, s);
+    const int* cs = csc ? csc->col_start.as<int>() : h->col_start.as<int>();
+    const int* ce = csc ? csc->col_end.as<int>() : h->col_end.as<int>();
+    const void* occs = csc ? csc->occ_sorted.p : h->occ_sorted.p;
+    HotWs hws;
+    HotPart hp;
+    DFB_TRY(dfbh::hot_ws(h, U, nnz, &hws));
+    h->launches += launch_hot_prereduce(h->prm.V_dim, U, dU, cs, ce, occs, d_val != nullptr, h->p_row.as<float>(),
+                                        h->pxv.as<float>(), h->hot_split, hws, &hp, s);
+    int nl = launch_bwd_update(h->tab, h->prm, slot, u_vrow, U, dU, cs, ce, occs, d_val != nullptr, h->p_row.as<float>(),
+                               h->pxv.as<float>(), flags, 1, nullptr, hp.part ? &hp : nullptr, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "sorted scatter unsupported for this V_dim");
     h->launches += nl;
     h->launches += launch_initv(h->tab, h->prm, slot, U, dU, flags, pos, s);
@@ -532,6 +553,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     else if (k == "overlap_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->overlap_auc = (int)x; }
     else if (k == "lookup_ilp") { if (!need_int(1, 4)) { delete h; return DFB_ERR_PARAM; } g_lookup_ilp = (int)x; }
     else if (k == "lookup_ctas") { if (!need_int(1, 64)) { delete h; return DFB_ERR_PARAM; } g_lookup_ctas = (int)x; }
+    else if (k == "hot_split") { if (!need_int(0, 1 << 30)) { delete h; return DFB_ERR_PARAM; } h->hot_split = (int)x; }
     else if (k == "l2_hints") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->l2_hints = (int)x; }
     else if (k == "id_bits") { if (!need_int(0, 64)) { delete h; return DFB_ERR_PARAM; } h->id_bits = (int)x; }
     else if (k == "shard_timeout_ms") { if (!need_int(1, 3600000)) { delete h; return DFB_ERR_PARAM; } h->shard_timeout_ms = x; }
@@ -618,7 +640,7 @@ int dfb_destroy(dfb_handle h) {
   }
   if (h->loc_stream) cudaStreamDestroy(h->loc_stream);
   DevBuf* bufs[] = {&h->u_wv, &h->l_rkeys, &h->l_skeys, &h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow,
-                    &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
+                    &h->hot_map, &h->hot_info, &h->hot_part, &h->hot_ps, &h->hot_cnt, &h->l_tmp, &h->auc_tmp, &h->pxv, &h->p_row, &h->occ, &h->occ_sorted, &h->lidx_sorted, &h->col_start, &h->col_end,
                     &h->keys, &h->cnt, &h->slot, &h->u_w, &h->u_vrow, &h->flags, &h->pos, &h->lens, &h->cub,
                     &h->gw, &h->gxxp, &h->gV, &h->pred, &h->vals, &h->auc_k, &h->auc_v, &h->a_off, &h->a_idx,
                     &h->a_val, &h->a_lab, &h->a_w, &h->a_wpos, &h->a_vpos, &h->a_pred, &h->a_grad, &h->scal,

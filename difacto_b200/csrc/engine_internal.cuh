@@ -30,6 +30,7 @@ struct dfb_engine {
   int id_bits = 0;          // > 0: feature ids are < 2^id_bits (fixes the radix-sort bit range of the GPU localizer)
   int loc_begin_bit = -1;   // auto mode: lowest significant bit of the reversed keys seen so far (sticky)
   long long shard_timeout_ms = 20000;
+  int hot_split = 4096;     // occurrence lists longer than this are pre-reduced in chunks by separate warps (0: off)
   cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
   cudaEvent_t ev_fm_done = nullptr, ev_auc_done = nullptr;
   dfb::Table tab;
@@ -42,6 +43,7 @@ struct dfb_engine {
   DevBuf keys, cnt, slot, u_w, u_vrow, flags, pos, lens, cub, gw, gxxp, gV, pred, vals;
   DevBuf auc_k, auc_v, auc_tmp;
   DevBuf pxv, p_row, occ, occ_sorted, lidx_sorted, col_start, col_end;
+  DevBuf hot_map, hot_info, hot_part, hot_ps, hot_cnt;
   DevBuf l_rkeys, l_skeys, l_pos, l_spos, l_head, l_rank, l_nnzrow, l_tmp;
   // outputs of the GPU localizer, double-buffered: the localizer of batch t+1 runs on loc_stream
   // while the step of batch t (which reads set t) runs on the main stream
@@ -132,6 +134,8 @@ struct StageTimer {
 // host-side helpers defined in engine.cu and used by shard.cu
 namespace dfbh {
 int prof_drain(dfb_engine* h);
+// workspaces of the hot-key pre-reduction for a batch of nkeys keys / nnz non-zeros (hot_split > 0)
+int hot_ws(dfb_engine* h, size_t nkeys, size_t nnz, dfb::HotWs* ws);
 int join_streams(dfb_engine* h);        // make the main stream wait for everything enqueued on the others
 int ensure_key_ws(dfb_engine* h, size_t n);
 // Localizer::Compact on the device into L (no host synchronisation unless need_host_U):

@@ -669,7 +669,8 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
                                                     const float* __restrict__ pxv, int* __restrict__ flags,
                                                     int acc_pen, float* __restrict__ gw_out,
                                                     const float* __restrict__ V_pulled,
-                                                    float* __restrict__ gV_out, SegDst seg, ShardApply sa) {
+                                                    float* __restrict__ gV_out, SegDst seg, ShardApply sa,
+                                                    HotPart hp) {
   const unsigned n = (unsigned)dev_count(n_cap, dn);     // < 2^31 (checked by the host): 32-bit index math
   constexpr int LPR = K / 4;
   constexpr int G = 32 / LPR;
@@ -736,6 +737,14 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
         hm &= hm - 1;
         const int ho0 = __shfl_sync(kFull, o0, hl), ho1 = __shfl_sync(kFull, o1, hl);
         float a = 0.f, b2 = 0.f;
+        int first = -1;
+        if (hp.part != nullptr && ho1 - ho0 > hp.split) first = hp.hotmap[base + (unsigned)hl];
+        if (first >= 0) {      // pre-reduced in chunks (k_hot_reduce): add the chunk partials in chunk order
+          if (lane == 0) {
+            const int nch = (ho1 - ho0 + hp.chunk - 1) / hp.chunk;
+            for (int c = 0; c < nch; ++c) { const float2 ps = hp.part_s[first + c]; a += ps.x; b2 += ps.y; }
+          }
+        } else
         for (int o = ho0 + lane; o < ho1; o += 32) {
           uint32_t row; float x;
           load_occ<HAS_VAL>(occ, o, row, x);
@@ -887,6 +896,17 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
         float4 acc[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int first = -1;
+        if (hp.part != nullptr && ho1 - ho0 > hp.split) first = hp.hotmap[ik];
+        if (first >= 0) {      // pre-reduced in chunks: chunk partials in chunk order
+          if (grp == 0) {
+            const int nch = (ho1 - ho0 + hp.chunk - 1) / hp.chunk;
+            for (int c = 0; c < nch; ++c) {
+              const float4 tp = __ldg(reinterpret_cast<const float4*>(hp.part + (size_t)(first + c) * K + sub * 4));
+              acc[0].x += tp.x; acc[0].y += tp.y; acc[0].z += tp.z; acc[0].w += tp.w;
+            }
+          }
+        } else
         for (int o = ho0 + grp; o < ho1; o += 4 * G) {    // G row-groups x 4 rows in flight
           float4 tt[4]; float xs[4];
 #pragma unroll
@@ -941,6 +961,78 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
   if (acc_pen) {
     pen = warp_sum(pen);
     if (lane == 0 && pen != 0.f) atomicAdd(&t.prog->penalty, (double)pen);
+  }
+}
+
+// ---- pre-reduction of the very hot keys (see HotPart) ----
+__global__ void k_hot_find(const int* __restrict__ col_start, const int* __restrict__ col_end, size_t n_cap,
+                           const unsigned long long* __restrict__ dn, int split, int chunk, HotWs ws) {
+  const size_t n = dev_count(n_cap, dn);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int o0 = col_start[i], o1 = col_end[i];
+    if (o1 - o0 <= split) continue;
+    const int nch = (o1 - o0 + chunk - 1) / chunk;
+    const unsigned long long first = atomicAdd(ws.counter, (unsigned long long)nch);
+    if (first + (unsigned long long)nch > (unsigned long long)ws.cap) { ws.hotmap[i] = -1; continue; }   // falls back to one warp
+    ws.hotmap[i] = (int)first;
+    for (int c = 0; c < nch; ++c) {
+      const int b = o0 + c * chunk;
+      ws.info[first + c] = make_int2(b, b + chunk < o1 ? b + chunk : o1);
+    }
+  }
+}
+
+template <int K, bool HAS_VAL>
+__global__ void __launch_bounds__(256) k_hot_reduce(const void* __restrict__ occ, const float* __restrict__ p_row,
+                                                    const float* __restrict__ pxv, HotWs ws) {
+  constexpr int LPR = K / 4;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long nch = *ws.counter;
+  if (nch > (unsigned long long)ws.cap) nch = 0;     // overflow: nothing was registered consistently beyond cap
+  for (unsigned c = warp0; c < (unsigned)nch; c += nwarps) {
+    const int2 be = ws.info[c];
+    float a = 0.f, b2 = 0.f;
+    for (int o = be.x + lane; o < be.y; o += 32) {
+      uint32_t row; float x;
+      load_occ<HAS_VAL>(occ, o, row, x);
+      const float pr = __ldg(p_row + row);
+      a = fmaf(pr, x, a);
+      if (HAS_VAL) b2 = fmaf(pr, x * x, b2);
+    }
+    a = warp_sum(a);
+    if (HAS_VAL) b2 = warp_sum(b2);
+    float4 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int o = be.x + grp; o < be.y; o += 4 * G) {
+      float4 tt[4]; float xs[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        xs[r] = 0.f; tt[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o + r * G < be.y) {
+          uint32_t row;
+          load_occ<HAS_VAL>(occ, o + r * G, row, xs[r]);
+          tt[r] = __ldg(reinterpret_cast<const float4*>(pxv + (size_t)row * K + sub * 4));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r].x = fmaf(tt[r].x, xs[r], acc[r].x); acc[r].y = fmaf(tt[r].y, xs[r], acc[r].y);
+        acc[r].z = fmaf(tt[r].z, xs[r], acc[r].z); acc[r].w = fmaf(tt[r].w, xs[r], acc[r].w);
+      }
+    }
+    float4 hg = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                            (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      hg.x += __shfl_xor_sync(kFull, hg.x, o); hg.y += __shfl_xor_sync(kFull, hg.y, o);
+      hg.z += __shfl_xor_sync(kFull, hg.z, o); hg.w += __shfl_xor_sync(kFull, hg.w, o);
+    }
+    if (grp == 0) *reinterpret_cast<float4*>(ws.part + (size_t)c * K + sub * 4) = hg;
+    if (lane == 0) ws.part_s[c] = make_float2(a, HAS_VAL ? b2 : a);
   }
 }
 
@@ -1134,16 +1226,19 @@ int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t 
 int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,
                       const unsigned long long* dn, const int* col_start, const int* col_end,
                       const void* occ_sorted, bool valued, const float* p_row, const float* pxv, int* flags,
-                      int acc_pen, const ShardApply* shard, cudaStream_t s) {
+                      int acc_pen, const ShardApply* shard, const HotPart* hot, cudaStream_t s) {
   if (n == 0) return 0;
   SegDst noseg;
   memset(&noseg, 0, sizeof(noseg));
   ShardApply sa;
   memset(&sa, 0, sizeof(sa));
   if (shard) sa = *shard;
+  HotPart hp;
+  memset(&hp, 0, sizeof(hp));
+  if (hot) hp = *hot;
 #define DFB_BU_(K, VAL, SRC)                                                                                   \
   k_bwd_update<K, VAL, true, SRC><<<grid, 256, 0, s>>>(t, p, slot, pull_vrow, n, dn, col_start, col_end, occ_sorted, \
-                                                       p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg, sa)
+                                                       p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg, sa, hp)
 #define DFB_BU(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
@@ -1162,6 +1257,33 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
   return -1;
 }
 
+int launch_hot_prereduce(int V_dim, size_t n, const unsigned long long* dn, const int* col_start, const int* col_end,
+                         const void* occ_sorted, bool valued, const float* p_row, const float* pxv, int split,
+                         const HotWs& ws, HotPart* hp, cudaStream_t s) {
+  memset(hp, 0, sizeof(*hp));
+  if (n == 0 || split <= 0) return 0;
+  const int chunk = split / 2 > 32 ? split / 2 : 32;
+  cudaMemsetAsync(ws.counter, 0, sizeof(unsigned long long), s);
+  k_hot_find<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(col_start, col_end, n, dn, split, chunk, ws);
+  const int grid = 148 * 4;
+#define DFB_HR(K)                                                                        \
+  do {                                                                                   \
+    if (valued) k_hot_reduce<K, true><<<grid, 256, 0, s>>>(occ_sorted, p_row, pxv, ws);  \
+    else        k_hot_reduce<K, false><<<grid, 256, 0, s>>>(occ_sorted, p_row, pxv, ws); \
+  } while (0)
+  switch (V_dim) {
+    case 8: DFB_HR(8); break;
+    case 16: DFB_HR(16); break;
+    case 32: DFB_HR(32); break;
+    case 64: DFB_HR(64); break;
+    case 128: DFB_HR(128); break;
+    default: return 0;
+  }
+#undef DFB_HR
+  hp->hotmap = ws.hotmap; hp->part = ws.part; hp->part_s = ws.part_s; hp->split = split; hp->chunk = chunk;
+  return 2;
+}
+
 int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_pulled, const int* hasv, size_t n,
                      const int* col_start, const int* col_end, const void* occ_sorted, bool valued,
                      const float* p_row, const float* pxv, float* gw_out, const float* V_pulled, float* gV_out,
@@ -1175,13 +1297,15 @@ int launch_bwd_dense(const Params& p, DevProgress* prog, int ks, const float* w_
   const int* w_alias = reinterpret_cast<const int*>(w_pulled);
   ShardApply nosa;
   memset(&nosa, 0, sizeof(nosa));
+  HotPart nohp;
+  memset(&nohp, 0, sizeof(nohp));
 #define DFB_BD(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
     if (valued) k_bwd_update<K, true, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, nullptr, col_start, col_end, \
-                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd, nosa);           \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd, nosa, nohp);     \
     else k_bwd_update<K, false, false><<<grid, 256, 0, s>>>(t, p, w_alias, hasv, n, nullptr, col_start, col_end, \
-                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd, nosa);           \
+                   occ_sorted, p_row, pxv, nullptr, acc_pen, gw_out, V_pulled, gV_out, sd, nosa, nohp);     \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_BD(8); return 1;
@@ -1203,11 +1327,13 @@ int launch_update_pushed(Table& t, const Params& p, const int* slot, const int* 
   memset(&noseg, 0, sizeof(noseg));
   ShardApply nosa;
   memset(&nosa, 0, sizeof(nosa));
+  HotPart nohp;
+  memset(&nohp, 0, sizeof(nohp));
 #define DFB_UP(K)                                                                                          \
   do {                                                                                                     \
     const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
     k_bwd_update<K, false, true, 1><<<grid, 256, 0, s>>>(t, p, slot, hasv, n, nullptr, nullptr, nullptr, nullptr, gw, \
-                                                          gV, flags, 0, nullptr, nullptr, nullptr, noseg, nosa); \
+                                                          gV, flags, 0, nullptr, nullptr, nullptr, noseg, nosa, nohp); \
   } while (0)
   switch (p.V_dim) {
     case 8: DFB_UP(8); return 1;

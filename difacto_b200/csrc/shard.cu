@@ -279,10 +279,16 @@ int shard_phase(dfb_engine* h, int phase) {
       ap.w_pulled = la.w + o;
       ap.conf = la.stamp ? sh.conf.as<unsigned char>() + o : nullptr;
       ap.vsave = sh.vsave.as<float>() + o * (size_t)K;
+      const void* occ_r = lay.at<void>(mine, lay.off_occ, lay.str_occ, d, r);
+      const float* p_r = lay.at<float>(mine, lay.off_p, lay.str_p, d, r);
+      const float* pxv_r = lay.at<float>(mine, lay.off_pxv, lay.str_pxv, d, r);
+      HotWs hws;
+      HotPart hp;
+      DFB_TRY(dfbh::hot_ws(h, Kseg, lay.Nseg, &hws));
+      h->launches += launch_hot_prereduce(K, Kseg, &hdr[r]->nkeys, cstart, cstart + 1, occ_r, valued, p_r, pxv_r,
+                                          h->hot_split, hws, &hp, O);
       int nl = launch_bwd_update(tt, h->prm, la.slot + o, la.vrow + o, Kseg, &hdr[r]->nkeys, cstart, cstart + 1,
-                                 lay.at<void>(mine, lay.off_occ, lay.str_occ, d, r), valued,
-                                 lay.at<float>(mine, lay.off_p, lay.str_p, d, r),
-                                 lay.at<float>(mine, lay.off_pxv, lay.str_pxv, d, r), flags, 1, &ap, O);
+                                 occ_r, valued, p_r, pxv_r, flags, 1, &ap, hp.part ? &hp : nullptr, O);
       if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
       h->launches += nl;
       h->launches += launch_initv(h->tab, h->prm, la.slot + o, Kseg, &hdr[r]->nkeys, flags, ws, O);

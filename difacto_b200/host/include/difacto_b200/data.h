@@ -89,15 +89,18 @@ class LibsvmPartReader {
 class BatchReader {
  public:
   BatchReader(const std::string& uri, const std::string& format, unsigned part, unsigned nparts,
-              unsigned batch_size, unsigned shuffle_buf_size = 0, float neg_sampling = 1.0f)
-      : batch_size_(batch_size), shuf_buf_(shuffle_buf_size), neg_sampling_(neg_sampling) {
+              unsigned batch_size, unsigned shuffle_buf_size = 0, float neg_sampling = 1.0f, unsigned epoch = 0)
+      : batch_size_(batch_size), shuf_buf_(shuffle_buf_size), neg_sampling_(neg_sampling),
+        seed_(epoch * 2654435761u + part) {
     if (format != "libsvm") throw Error("unknown format " + format + " (this build reads libsvm)");
     if (shuf_buf_) DFB_CHECK(shuf_buf_ >= batch_size_);
     LibsvmPartReader(uri, part, nparts).ParseAll(&all_);
     order_.resize(all_.Size());
     std::iota(order_.begin(), order_.end(), 0u);
     if (shuf_buf_) {
-      std::mt19937 gen(0);
+      // the reference's std::random_shuffle advances one global generator, so every epoch sees another order;
+      // here the order is a function of (epoch, part): different per epoch, reproducible per run
+      std::mt19937 gen(epoch * 2654435761u + part * 40503u + 1u);
       for (size_t b = 0; b < order_.size(); b += shuf_buf_) {
         const size_t e = std::min(order_.size(), b + shuf_buf_);
         std::shuffle(order_.begin() + static_cast<std::ptrdiff_t>(b), order_.begin() + static_cast<std::ptrdiff_t>(e), gen);
@@ -129,10 +132,10 @@ class BatchReader {
  private:
   unsigned batch_size_, shuf_buf_;
   float neg_sampling_;
+  unsigned int seed_;
   RowBlockContainer<feaid_t> all_, batch_;
   std::vector<unsigned> order_;
   size_t cursor_ = 0;
-  unsigned int seed_ = 0;
 };
 
 /**

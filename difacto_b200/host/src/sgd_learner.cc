@@ -214,7 +214,7 @@ void SGDLearner::IterateData(const sgd::Job& job, sgd::Progress* progress) {
                      static_cast<unsigned>(job.part_idx), static_cast<unsigned>(job.num_parts),
                      train ? static_cast<unsigned>(param_.batch_size) : 65536u,
                      train ? static_cast<unsigned>(param_.batch_size) * static_cast<unsigned>(param_.shuffle) : 0u,
-                     train ? param_.neg_sampling : 1.0f);
+                     train ? param_.neg_sampling : 1.0f, static_cast<unsigned>(job.epoch));
   while (reader.Next()) {
     const bool push_cnt = train && job.epoch == 0;   // :201-202
     if (param_.fused == 1) {

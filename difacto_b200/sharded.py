@@ -22,6 +22,7 @@ concatenation of what comes back from owners 0..S-1 is already in key order: no 
 The protocol is backend-agnostic: `CudaBackend` drives the sm_100a engine (the product);
 tests/ injects a CPU backend over gloo to check the protocol itself against the oracle.
 """
+import contextlib
 import os
 import time
 
@@ -58,6 +59,11 @@ class CudaBackend:
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def stream_ctx(self):
+        """the engine's kernels run on the engine's stream; torch's collectives, barriers and allocations are ordered
+        against torch's CURRENT stream: a step must run with the engine's stream current"""
+        return torch.cuda.stream(self.stream)
 
     def feacnt(self, keys, cnt):
         if len(keys):
@@ -128,10 +134,19 @@ class ShardedStore:
         else:
             dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
 
+    def _ctx(self):
+        ctx = getattr(self.b, "stream_ctx", None)
+        return ctx() if ctx else contextlib.nullcontext()
+
     def step(self, batch, is_train=True, push_cnt=False):
-        """one minibatch of SGDLearner::IterateData on this rank's batch; collective over ranks.
+        """one minibatch of SGDLearner::IterateData on this rank's batch; collective over ranks.  Runs with the
+        backend's stream current (the collectives and the engine's kernels must share one stream order).
 
         batch: dict(nrows, nnz, U, off, lidx, val|None, lab, keys, cnt|None, bounds[S+1])"""
+        with self._ctx():
+            return self._step(batch, is_train, push_cnt)
+
+    def _step(self, batch, is_train=True, push_cnt=False):
         S, U, ks = self.S, batch["U"], self.ks
         self._mark("begin")
         bounds = batch["bounds"]
@@ -233,7 +248,7 @@ class PeerShardedStore(ShardedStore):
         if self.S > 1:
             dist.all_reduce(self._tick, group=self.group)
 
-    def step(self, batch, is_train=True, push_cnt=False):
+    def _step(self, batch, is_train=True, push_cnt=False):
         S, U, ks, me, E = self.S, batch["U"], self.ks, self.rank, self.b.E
         self._mark("begin")
         bounds = [int(x) for x in batch["bounds"]]

@@ -184,9 +184,9 @@ def test_param_errors_mirror_dmlc():
 # ----------------------------------------------------------------------------------------
 # (B) fused step vs the oracle's IterateData, whole trajectories
 # ----------------------------------------------------------------------------------------
-def run_both(kw, batches, epochs, force_generic=0, feacnt_epochs=1, val_every=0, scatter="sorted"):
+def run_both(kw, batches, epochs, force_generic=0, feacnt_epochs=1, val_every=0, scatter="sorted", **engine_kw):
     M = O.Oracle(**kw)
-    E = engine(force_generic=force_generic, scatter=scatter, **kw)
+    E = engine(force_generic=force_generic, scatter=scatter, **engine_kw, **kw)
     t = 0
     for ep in range(epochs):
         for (o, l, i, v) in batches:
@@ -277,6 +277,29 @@ def test_fused_trajectory_vs_oracle(V_dim, valued, force_generic, scatter):
     assert E.rng_state() == M.seed()
     if V_dim:
         assert (ohasv == 1).sum() > 10
+
+
+def test_very_hot_keys_prereduced_in_chunks_vs_oracle():
+    """occurrence lists longer than hot_split are cut into chunks reduced by separate warps (k_hot_reduce) and the
+    partials added in chunk order: a feature present in EVERY row (the Criteo case), a threshold low enough
+    that the ~400-occurrence keys take the path too, binary and valued batches, the fused and the sharded kernel"""
+    rng = np.random.default_rng(99)
+    kw = dict(V_dim=16, l1=0.01, l2=0.01, lr=0.05, V_lr=0.02, V_threshold=0, V_l2=0.02, V_init_scale=0.1, seed=8)
+    batches = []
+    for valued in (False, True, False):
+        b = rand_batch(rng, 3000, 12, 25, valued, min_nnz=4)
+        b[2][b[0][:-1].astype(np.int64)] = np.uint64(77) * np.uint64(0x9E3779B97F4A7C15)     # first nnz of every row: one feature
+        batches.append(b)
+    M, E = run_both(kw, batches, epochs=2, val_every=0, hot_split=100)
+    keys = np.unique(np.concatenate([O.reverse_bytes_np(b[2]) for b in batches]))
+    compare_state(M, E, keys, tol=dict(rtol=2e-3, atol=2e-5))
+    # bit-reproducible, and the default threshold (the same lists reduced by one warp each) agrees within rounding
+    E2 = run_both(kw, batches, epochs=2, val_every=0, hot_split=100)[1]
+    for a, b in zip(E.read_entries(keys), E2.read_entries(keys)):
+        assert np.array_equal(a, b)
+    E3 = run_both(kw, batches, epochs=2, val_every=0, hot_split=0)[1]
+    for a, b in zip(E.read_entries(keys), E3.read_entries(keys)):
+        assert_close(a, b, what="pre-reduced vs one warp", rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("V_dim,valued", [(16, True), (64, False), (128, True)])
