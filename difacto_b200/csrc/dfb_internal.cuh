@@ -173,6 +173,9 @@ bool fm_fast_supported(int V_dim);
 // ---- launchers (kernels_fm.cu) ----
 // returns number of kernel launches performed, or <0 on invalid configuration
 int launch_fm(const FmBatch& b, const FmView& v, int force_generic, cudaStream_t s);
+// the bulk-copy (cp.async.bulk / UBLKCP) variant of the predict kernel for V_dim = 64 (kernels_fm_tma.cu, an A/B);
+// returns 0 when the configuration is outside the experiment
+int launch_fm_tma_predict(const FmBatch& b, const FmView& v, cudaStream_t s);
 // MODE 3: partial interaction sums of every source's rows (see PartArgs); v.vbase/vstride = the table rows
 int launch_fm_partial(int V_dim, bool valued, const FmView& v, const PartArgs& pa, cudaStream_t s);
 int launch_grad_finalize(int V_dim, size_t nkeys, const float* weights, const int* V_pos,
@@ -235,10 +238,11 @@ int launch_read_entries(Table& t, const int* slot, size_t n, float* scal, int* h
 
 // ---- GPU localizer (kernels_localize.cu): Localizer::Compact + the CSC view from one radix sort ----
 size_t localize_sort_tmp_bytes(size_t nnz);
+// hi32: sort on the upper 32 key bits only (the caller knows the lower 32 are zero: ids < 2^32); verified on the device
 int launch_localize_keys(const uint64_t* ids, size_t nnz, uint64_t max_index, unsigned long long* rkeys,
                          uint32_t* pos, unsigned long long* or_all, const uint64_t* offset, size_t nrows,
-                         uint32_t* nnz_row, cudaStream_t s);
-int launch_localize_sort(const unsigned long long* rkeys, const uint32_t* pos, size_t nnz, int begin_bit,
+                         uint32_t* nnz_row, bool hi32, cudaStream_t s);
+int launch_localize_sort(const unsigned long long* rkeys, const uint32_t* pos, size_t nnz, int begin_bit, bool hi32,
                          unsigned long long* skeys, uint32_t* spos, int* head, int* rank1, void* tmp,
                          size_t tmp_bytes, const uint32_t* nnz_row, const float* value, uint64_t* keys_out,
                          int* col_start, int* col_end, uint32_t* lidx_out, void* occ_sorted,
@@ -252,7 +256,7 @@ int launch_cnt_from_cols(const int* col_start, const int* col_end, size_t n, flo
 size_t csc_tmp_bytes(size_t nnz, bool valued);
 int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t nnz, size_t nkeys,
                      uint32_t* lidx_sorted, void* occ_sorted, int* col_start, int* col_end,
-                     void* cub_tmp, size_t cub_bytes, cudaStream_t s);
+                     void* cub_tmp, size_t cub_bytes, DevProgress* prog, cudaStream_t s);
 // per key: grad = sum_occ x * pXV[row] - V * XXp, then either FTRL/AdaGrad in place (apply) or
 // complete dense gradient rows out (gw_out, gV_out = sum - V_pulled*XXp; the sharded worker).
 int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pull_vrow, size_t n,

@@ -275,7 +275,9 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   }
   if (nrows) {
     StageTimer tm(h, 1);
-    int nl = launch_fm(b, v, h->force_generic, s);
+    int nl = 0;
+    if (h->k1_tma && !is_train && !h->force_generic) nl = launch_fm_tma_predict(b, v, s);
+    if (nl == 0) nl = launch_fm(b, v, h->force_generic, s);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported FM configuration");
     h->launches += nl;
   }
@@ -304,10 +306,13 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
     // CalcGrad + Push(kGradient) without materialising the gradient: CSC view of the batch, then
     // per key reduce + FTRL + AdaGrad (+ the -V*XXp term and the penalty of the pulled weights)
     StageTimer tm(h, 3);
-    if (!csc_ready)
-      h->launches += launch_csc_build(d_idx, h->occ.p, d_val != nullptr, nnz, U, h->lidx_sorted.as<uint32_t>(),
-                                      h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
-                                      h->cub.bytes, s);
+    if (!csc_ready) {
+      int nl = launch_csc_build(d_idx, h->occ.p, d_val != nullptr, nnz, U, h->lidx_sorted.as<uint32_t>(),
+                                h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
+                                h->cub.bytes, h->tab.prog, s);
+      if (nl < 0) return h->fail(DFB_ERR_CUDA, "CSC sort of the batch failed (temporary storage)");
+      h->launches += nl;
+    }
   }
   StageTimer tm_upd(h, 4);
   if (sorted) {
@@ -398,9 +403,7 @@ int dfbh::localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* 
     DFB_CUDA(h, cudaMemsetAsync(scal, 0, 16, s));
     return 0;
   }
-  h->launches += launch_localize_keys(d_ids, nnz, max_index, h->l_rkeys.as<unsigned long long>(),
-                                      h->l_pos.as<uint32_t>(), scal, d_off, nrows, h->l_nnzrow.as<uint32_t>(), s);
-  // ---- the bit range of the sort ----
+  // ---- the bit range of the sort (known before the keys are produced, unless this batch must be measured) ----
   int begin_bit = -1;
   const bool restricted = max_index != ~0ULL;        // Localizer(max_index) of dfb_localize: range unknown
   if (h->id_bits > 0 && !restricted) {
@@ -414,6 +417,9 @@ int dfbh::localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* 
       }
     begin_bit = h->loc_begin_bit;
   }
+  const bool hi32 = begin_bit >= 32;       // only the upper 32 key bits can be set: 32-bit sort keys
+  h->launches += launch_localize_keys(d_ids, nnz, max_index, h->l_rkeys.as<unsigned long long>(),
+                                      h->l_pos.as<uint32_t>(), scal, d_off, nrows, h->l_nnzrow.as<uint32_t>(), hi32, s);
   if (begin_bit < 0) {
     DFB_CUDA(h, cudaMemcpyAsync(h->h_scal, scal, 8, cudaMemcpyDeviceToHost, s));
     DFB_CUDA(h, cudaStreamSynchronize(s));
@@ -427,12 +433,16 @@ int dfbh::localize_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* 
       h->or_pending[q] = true;
     }
   }
-  h->launches += launch_localize_sort(h->l_rkeys.as<unsigned long long>(), h->l_pos.as<uint32_t>(), nnz, begin_bit,
-                                      h->l_skeys.as<unsigned long long>(), h->l_spos.as<uint32_t>(),
-                                      h->l_head.as<int>(), h->l_rank.as<int>(), h->l_tmp.p, h->l_tmp.bytes,
-                                      h->l_nnzrow.as<uint32_t>(), d_val, L.keys.as<uint64_t>(),
-                                      L.col_start.as<int>(), L.col_end.as<int>(), L.lidx.as<uint32_t>(),
-                                      L.occ_sorted.p, scal, h->tab.prog, s);
+  {
+    int nl = launch_localize_sort(h->l_rkeys.as<unsigned long long>(), h->l_pos.as<uint32_t>(), nnz, begin_bit, hi32,
+                                  h->l_skeys.as<unsigned long long>(), h->l_spos.as<uint32_t>(),
+                                  h->l_head.as<int>(), h->l_rank.as<int>(), h->l_tmp.p, h->l_tmp.bytes,
+                                  h->l_nnzrow.as<uint32_t>(), d_val, L.keys.as<uint64_t>(),
+                                  L.col_start.as<int>(), L.col_end.as<int>(), L.lidx.as<uint32_t>(),
+                                  L.occ_sorted.p, scal, h->tab.prog, s);
+    if (nl < 0) return h->fail(DFB_ERR_CUDA, "radix sort / scan of the GPU localizer failed (temporary storage)");
+    h->launches += nl;
+  }
   if (need_host_U) {
     DFB_CUDA(h, cudaMemcpyAsync(h->h_scal + 1, scal + 1, 8, cudaMemcpyDeviceToHost, s));
     DFB_CUDA(h, cudaStreamSynchronize(s));
@@ -553,6 +563,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     else if (k == "overlap_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->overlap_auc = (int)x; }
     else if (k == "lookup_ilp") { if (!need_int(1, 4)) { delete h; return DFB_ERR_PARAM; } g_lookup_ilp = (int)x; }
     else if (k == "lookup_ctas") { if (!need_int(1, 64)) { delete h; return DFB_ERR_PARAM; } g_lookup_ctas = (int)x; }
+    else if (k == "k1_tma") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->k1_tma = (int)x; }
     else if (k == "hot_split") { if (!need_int(0, 1 << 30)) { delete h; return DFB_ERR_PARAM; } h->hot_split = (int)x; }
     else if (k == "l2_hints") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->l2_hints = (int)x; }
     else if (k == "id_bits") { if (!need_int(0, 64)) { delete h; return DFB_ERR_PARAM; } h->id_bits = (int)x; }
@@ -1541,9 +1552,13 @@ static int dev_fm_step_impl(dfb_handle h, size_t nrows, size_t nnz, const uint64
     h->launches += nl;
   }
   if (sorted) {
-    h->launches += launch_csc_build(d_index, h->occ.p, d_value != nullptr, nnz, nkeys, h->lidx_sorted.as<uint32_t>(),
-                                    h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
-                                    h->cub.bytes, s);
+    {
+      int nlc = launch_csc_build(d_index, h->occ.p, d_value != nullptr, nnz, nkeys, h->lidx_sorted.as<uint32_t>(),
+                                 h->occ_sorted.p, h->col_start.as<int>(), h->col_end.as<int>(), h->cub.p,
+                                 h->cub.bytes, h->tab.prog, s);
+      if (nlc < 0) return h->fail(DFB_ERR_CUDA, "CSC sort of the batch failed (temporary storage)");
+      h->launches += nlc;
+    }
     // the penalty of the pulled weights (sgd_learner.cc:148) is accumulated by the same kernel
     int nl = launch_bwd_dense(h->prm, h->tab.prog, ks, d_w, d_hasv, nkeys, h->col_start.as<int>(),
                               h->col_end.as<int>(), h->occ_sorted.p, d_value != nullptr, h->p_row.as<float>(),

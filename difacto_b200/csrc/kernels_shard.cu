@@ -178,10 +178,12 @@ __global__ void __launch_bounds__(1024) k_shard_rowscan(int* __restrict__ cnt, s
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  for (size_t b0 = 0; b0 < nrows; b0 += blockDim.x) {
-    const size_t i = b0 + threadIdx.x;
-    const int v = i < nrows ? c[i] : 0;
-    int x = v;
+  for (size_t b0 = 0; b0 < nrows; b0 += (size_t)blockDim.x * 8) {     // 8 consecutive rows per thread
+    const size_t i0 = b0 + (size_t)threadIdx.x * 8;
+    int v[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = i0 + q < nrows ? c[i0 + q] : 0; sum += v[q]; }
+    int x = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(kFullMask, x, o);
@@ -200,8 +202,12 @@ __global__ void __launch_bounds__(1024) k_shard_rowscan(int* __restrict__ cnt, s
     }
     __syncthreads();
     const int carry = s_carry;
-    const int excl = carry + (wid ? s_warp[wid - 1] : 0) + (x - v);
-    if (i < nrows) { c[i] = excl; dst[i] = (uint64_t)excl; }
+    int run = carry + (wid ? s_warp[wid - 1] : 0) + (x - sum);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (i0 + q < nrows) { c[i0 + q] = run; dst[i0 + q] = (uint64_t)run; }
+      run += v[q];
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_carry = carry + s_warp[31];
     __syncthreads();

@@ -616,11 +616,14 @@ __global__ void __launch_bounds__(1024) k_auc_area(const float* __restrict__ sor
 // sorted (atomic-free) gradient reduction
 // ---------------------------------------------------------------------------------------
 // boundaries of the runs of equal key ids in the sorted id list
-__global__ void k_col_bounds(const uint32_t* __restrict__ sorted, size_t n, int* __restrict__ col_start,
-                             int* __restrict__ col_end) {
+__global__ void k_col_bounds(const uint32_t* __restrict__ sorted, size_t n, size_t nkeys, int* __restrict__ col_start,
+                             int* __restrict__ col_end, DevProgress* prog) {
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint32_t cur = sorted[j];
+  // a caller-provided local index outside [0, nkeys) would write out of bounds: report it instead (the sort
+  // only looks at ceil(log2 nkeys) bits, so such an index shows up here as a value >= nkeys or out of order)
+  if (cur >= nkeys || (j > 0 && sorted[j - 1] > cur)) { if (prog) raise(prog, DFB_ERR_INVALID); return; }
   if (j == 0) col_start[cur] = 0;
   else {
     const uint32_t prev = sorted[j - 1];
@@ -1185,7 +1188,8 @@ int launch_auc(const float* label, const float* pred, size_t n, float* key_tmp2,
                size_t cub_bytes, double* out_add, cudaStream_t s) {
   if (n == 0) return 0;
   // stable ascending radix sort by pred: ties keep original row order
-  cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, pred, key_tmp2, label, val_tmp2, (int)n, 0, 32, s);
+  if (cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, pred, key_tmp2, label, val_tmp2, (int)n, 0, 32, s) != cudaSuccess)
+    return -1;
   k_auc_area<<<1, 1024, 0, s>>>(val_tmp2, n, out_add);
   return 4;
 }
@@ -1205,21 +1209,25 @@ size_t csc_tmp_bytes(size_t nnz, bool valued) {
 
 int launch_csc_build(const uint32_t* lidx, const void* occ, bool valued, size_t nnz, size_t nkeys,
                      uint32_t* lidx_sorted, void* occ_sorted, int* col_start, int* col_end, void* cub_tmp,
-                     size_t cub_bytes, cudaStream_t s) {
+                     size_t cub_bytes, DevProgress* prog, cudaStream_t s) {
   if (nkeys == 0) return 0;
-  cudaMemsetAsync(col_start, 0, nkeys * sizeof(int), s);
-  cudaMemsetAsync(col_end, 0, nkeys * sizeof(int), s);
+  if (cudaMemsetAsync(col_start, 0, nkeys * sizeof(int), s) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(col_end, 0, nkeys * sizeof(int), s) != cudaSuccess) return -1;
   if (nnz == 0) return 0;
+  // all 32 bits take part when an index could be out of range; the common case sorts ceil(log2 nkeys) bits and
+  // k_col_bounds verifies the result (sortedness + range)
   const int eb = bits_for(nkeys);
+  cudaError_t e;
   if (valued)
-    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, lidx, lidx_sorted,
-                                    reinterpret_cast<const unsigned long long*>(occ),
-                                    reinterpret_cast<unsigned long long*>(occ_sorted), (int)nnz, 0, eb, s);
+    e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, lidx, lidx_sorted,
+                                        reinterpret_cast<const unsigned long long*>(occ),
+                                        reinterpret_cast<unsigned long long*>(occ_sorted), (int)nnz, 0, eb, s);
   else
-    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, lidx, lidx_sorted,
-                                    reinterpret_cast<const uint32_t*>(occ),
-                                    reinterpret_cast<uint32_t*>(occ_sorted), (int)nnz, 0, eb, s);
-  k_col_bounds<<<(int)((nnz + 255) / 256), 256, 0, s>>>(lidx_sorted, nnz, col_start, col_end);
+    e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, lidx, lidx_sorted,
+                                        reinterpret_cast<const uint32_t*>(occ),
+                                        reinterpret_cast<uint32_t*>(occ_sorted), (int)nnz, 0, eb, s);
+  if (e != cudaSuccess) return -1;
+  k_col_bounds<<<(int)((nnz + 255) / 256), 256, 0, s>>>(lidx_sorted, nnz, nkeys, col_start, col_end, prog);
   return 2 + (eb + 7) / 8;   // histogram + one onesweep pass per 8 key bits + bounds
 }
 
