@@ -140,30 +140,33 @@ __device__ __forceinline__ int owner_of(const ShardBounds& b, int S, uint32_t li
 }
 
 // the rows of the worker's CSR, split by owner of the column: per (owner, row) counts ...
+// (one __match_any per 32-nnz chunk groups the lanes by owner; the lowest lane of a group adds the group's size)
 __global__ void __launch_bounds__(256) k_shard_rowcount(const uint64_t* __restrict__ offset,
                                                         const uint32_t* __restrict__ lidx, size_t nrows,
                                                         const ShardBounds* __restrict__ wb, int S,
                                                         int* __restrict__ cnt /* [S][nrows+1] */) {
   __shared__ ShardBounds b;
+  __shared__ int s_cnt[8][8];          // [warp][owner]
   if (threadIdx.x == 0) b = *wb;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   for (size_t row = warp0; row < nrows; row += nwarps) {
     const uint64_t o0 = offset[row], o1 = offset[row + 1];
-    int c = 0;
+    if (lane < 8) s_cnt[wid][lane] = 0;
+    __syncwarp();
     if (b.valid) {
       for (uint64_t cc = o0; cc < o1; cc += 32) {
         const uint64_t j = cc + lane;
-        const int own = j < o1 ? owner_of(b, S, __ldg(lidx + j)) : -1;
-        for (int s = 0; s < S; ++s) {
-          const unsigned m = __ballot_sync(kFullMask, own == s);
-          if (lane == s) c += __popc(m);
-        }
+        const int own = j < o1 ? owner_of(b, S, __ldg(lidx + j)) : 8 + (lane & 7);   // inactive lanes: groups that are ignored
+        const unsigned peers = __match_any_sync(kFullMask, own);
+        if (own < 8 && lane == __ffs(peers) - 1) s_cnt[wid][own] += __popc(peers);
+        __syncwarp();
       }
     }
-    if (lane < S) cnt[(size_t)lane * (nrows + 1) + row] = c;
+    if (lane < S) cnt[(size_t)lane * (nrows + 1) + row] = s_cnt[wid][lane];
+    __syncwarp();
   }
 }
 
@@ -223,35 +226,36 @@ __global__ void __launch_bounds__(256) k_shard_fill(const uint64_t* __restrict__
                                                     const ShardBounds* __restrict__ wb, int S,
                                                     const int* __restrict__ rowptr /* [S][nrows+1] */, FillDst d) {
   __shared__ ShardBounds b;
+  __shared__ int s_pos[8][8];          // [warp][owner]: next free slot of the owner's sub-row
   if (threadIdx.x == 0) b = *wb;
   __syncthreads();
   if (!b.valid) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   for (size_t row = warp0; row < nrows; row += nwarps) {
     const uint64_t o0 = offset[row], o1 = offset[row + 1];
-    int pos = lane < S ? rowptr[(size_t)lane * (nrows + 1) + row] : 0;   // lane s: next free slot of owner s
+    if (lane < S) s_pos[wid][lane] = rowptr[(size_t)lane * (nrows + 1) + row];
+    __syncwarp();
     for (uint64_t cc = o0; cc < o1; cc += 32) {
       const uint64_t j = cc + lane;
       uint32_t u = 0;
       float x = 0.f;
-      int own = -1;
+      int own = 8 + (lane & 7);
       if (j < o1) {
         u = __ldg(lidx + j);
         if (HAS_VAL) x = __ldg(value + j);
         own = owner_of(b, S, u);
       }
-      for (int s = 0; s < S; ++s) {
-        const unsigned m = __ballot_sync(kFullMask, own == s);
-        const int base = __shfl_sync(kFullMask, pos, s);
-        if (own == s) {
-          const int at = base + __popc(m & ((1u << lane) - 1u));
-          d.ridx_dst[s][at] = u - (uint32_t)b.kb[s];
-          if (HAS_VAL) d.rval_dst[s][at] = x;
-        }
-        if (lane == s) pos += __popc(m);
+      const unsigned peers = __match_any_sync(kFullMask, own);
+      if (own < 8) {
+        const int at = s_pos[wid][own] + __popc(peers & ((1u << lane) - 1u));
+        d.ridx_dst[own][at] = u - (uint32_t)b.kb[own];
+        if (HAS_VAL) d.rval_dst[own][at] = x;
       }
+      __syncwarp();
+      if (own < 8 && lane == __ffs(peers) - 1) s_pos[wid][own] += __popc(peers);
+      __syncwarp();
     }
   }
 }

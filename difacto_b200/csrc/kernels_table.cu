@@ -768,7 +768,16 @@ __global__ void __launch_bounds__(256, DFB_BU_MINBLOCKS) k_bwd_update(Table t, P
         if (acc_pen) pen += pen_w(p, SRC == 2 ? sa.w_pulled[i] : sc.y);   // penalty of the PULLED weights (sgd_learner.cc:148)
         const bool became_nz = ftrl_step(p, gw, sc.y, sc.z, sc.w);
         *reinterpret_cast<float4*>(&e->fea_cnt) = sc;
-        flags[i] = (became_nz && p.V_dim > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
+        if (SRC == 2) {
+          // sharded store: InitV of all workers' updates runs once after the last one (same order of the random
+          // stream: worker-major, key order); vrow = -2 marks "row pending" so that a later worker's update in
+          // the same step neither uses nor re-requests it
+          const bool fl = became_nz && p.V_dim > 0 && e->vrow == -1 && sc.x > (float)p.V_threshold;
+          if (fl) e->vrow = -2;
+          flags[i] = fl ? 1 : 0;
+        } else {
+          flags[i] = (became_nz && p.V_dim > 0 && e->vrow < 0 && sc.x > (float)p.V_threshold) ? 1 : 0;
+        }
       } else if (active) {
         flags[i] = 0;
       }

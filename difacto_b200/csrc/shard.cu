@@ -267,6 +267,8 @@ int shard_phase(dfb_engine* h, int phase) {
   if (phase == 3) {
   // ------------------------------- O part 2: one Update per worker, rank order -------------------------------
   StageTimer tm_upd(h, 9, O);
+  // the InitV requests of all workers' updates: flags[S][Kseg], zero where no key is (one pass after the last update)
+  if (is_train) DFB_CUDA(h, cudaMemsetAsync(flags, 0, (size_t)S * Kseg * sizeof(int), O));
   for (int r = 0; r < S; ++r) {
     if (r == me) DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_reduce[d], 0));
     else h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_PXV, r), 8, 1u, fv, sh.timeout_cycles, h->tab.prog, O);
@@ -288,10 +290,9 @@ int shard_phase(dfb_engine* h, int phase) {
       h->launches += launch_hot_prereduce(K, Kseg, &hdr[r]->nkeys, cstart, cstart + 1, occ_r, valued, p_r, pxv_r,
                                           h->hot_split, hws, &hp, O);
       int nl = launch_bwd_update(tt, h->prm, la.slot + o, la.vrow + o, Kseg, &hdr[r]->nkeys, cstart, cstart + 1,
-                                 occ_r, valued, p_r, pxv_r, flags, 1, &ap, hp.part ? &hp : nullptr, O);
+                                 occ_r, valued, p_r, pxv_r, flags + o, 1, &ap, hp.part ? &hp : nullptr, O);
       if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
       h->launches += nl;
-      h->launches += launch_initv(h->tab, h->prm, la.slot + o, Kseg, &hdr[r]->nkeys, flags, ws, O);
     } else {
       h->launches += launch_penalty(h->prm, sh.src_prog(r), la.w + o, la.vrow + o, h->tab.V, h->tab.rs, 0, Kseg,
                                     &hdr[r]->nkeys, O);
@@ -299,6 +300,9 @@ int shard_phase(dfb_engine* h, int phase) {
     h->launches += launch_shard_done(sh.src_prog(r), h->tab.prog, lay.at<double>(sh.peer[r], lay.off_pen, lay.str_pen, d, me),
                                      lay.flag(sh.peer[r], ShardLayout::F_DONE, me), fv, O);
   }
+  // InitV (sgd_updater.cc:121-126,140-147) for the keys whose w left zero, in worker-major key order -- the order in
+  // which the reference's server would have met them
+  if (is_train) h->launches += launch_initv(h->tab, h->prm, la.slot, (size_t)S * Kseg, nullptr, flags, ws, O);
   tm_upd.stop();
   DFB_CUDA(h, cudaEventRecord(sh.ev_upd[d], O));
   }
@@ -403,8 +407,8 @@ int dfb_shard_init(dfb_handle h, int rank, int nranks, size_t max_rows, size_t m
   const size_t tot = (size_t)nranks * Kseg;
   int rc = 0;
   if ((rc = h->ensure(sh->wb, sizeof(ShardBounds))) || (rc = h->ensure(sh->slot, tot * 4)) || (rc = h->ensure(sh->w, tot * 4)) ||
-      (rc = h->ensure(sh->vrow, tot * 4)) || (rc = h->ensure(sh->wv, tot * 8)) || (rc = h->ensure(sh->flags, Kseg * 4)) ||
-      (rc = h->ensure(sh->ws, (Kseg / 32 + 64) * 4)))
+      (rc = h->ensure(sh->vrow, tot * 4)) || (rc = h->ensure(sh->wv, tot * 8)) || (rc = h->ensure(sh->flags, tot * 4)) ||
+      (rc = h->ensure(sh->ws, (tot / 32 + 64) * 4)))
     return fail(rc);
   if (nranks > 1 && ((rc = h->ensure(sh->conf, tot)) || (rc = h->ensure(sh->vsave, tot * (size_t)K * 4)))) return fail(rc);
   const size_t np = (size_t)nranks + 4;
