@@ -86,6 +86,10 @@ struct SGDLearnerParam {
   float neg_sampling = 1, stop_rel_objv = 1e-5f, stop_val_auc = 1e-5f;
   int fused = 1;   // engine-only: 1 = raw block -> one device call, 2 = host localizer + one device call,
                    // 0 = the reference's Pull/Predict/CalcGrad/Push plugin calls
+  int num_gpus = 1;          // engine-only: > 1 = the NVLink-sharded store over GPUs 0..num_gpus-1 (one worker thread
+                             // and one table shard per GPU, dfb_shard_*; needs fused = 1)
+  long long shard_max_nnz = 0;   // engine-only: capacity (non-zeros) of one minibatch in the sharded store;
+                                 // 0 = batch_size * 256
 
   KWArgs InitAllowUnknown(const KWArgs& kwargs) {
     KWArgs remain;
@@ -108,6 +112,8 @@ struct SGDLearnerParam {
         else if (k == "stop_rel_objv") stop_rel_objv = std::stof(v);
         else if (k == "stop_val_auc") stop_val_auc = std::stof(v);
         else if (k == "fused") fused = std::stoi(v);
+        else if (k == "num_gpus") num_gpus = std::stoi(v);
+        else if (k == "shard_max_nnz") shard_max_nnz = std::stoll(v);
         else remain.push_back(kv);
       } catch (const std::logic_error&) {
         throw ParamError("Invalid Parameter format for " + k + " value='" + v + "'");

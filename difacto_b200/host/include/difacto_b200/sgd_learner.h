@@ -7,9 +7,15 @@
 //   fused = 2: host Localizer::Compact, then one dfb_train_step per batch;
 //   fused = 0: the reference's own sequence of plugin calls Store::Pull -> GetPos -> Loss::Predict ->
 //              Evaluate -> penalty -> AUC -> Loss::CalcGrad -> Store::Push through the adapter classes.
+// num_gpus = N > 1 (with fused = 1): the worker/server split SGDLearner::RunEpoch was written for
+// (sgd_learner.cc:78-89): N worker threads, each reading its own file parts and owning GPU r's shard of the
+// model, one collective dfb_shard_step_async per round of minibatches (the NVLink-sharded store, csrc/shard.cu).
 #pragma once
 #include <cmath>
+#include <condition_variable>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -64,6 +70,10 @@ class SGDLearner : public Learner {
   void RunEpochs();
   void RunEpoch(int epoch, int job_type, sgd::Progress* prog);
   void IterateData(const sgd::Job& job, sgd::Progress* prog);
+  /** num_gpus > 1: one epoch over all N * num_jobs_per_epoch file parts, part i handled by worker i % N */
+  void RunEpochSharded(int epoch, int job_type, sgd::Progress* prog);
+  /** engine of GPU r (r = 0: the updater's own) */
+  const std::shared_ptr<GpuEngine>& ShardEngine(int r) { return r == 0 ? GetUpdater()->engine() : shard_engines_[r - 1]; }
   void BatchFused(const RowBlockContainer<unsigned>& data, const std::vector<feaid_t>& keys,
                   const std::vector<real_t>* cnt, bool train, sgd::Progress* prog);
   void BatchPluginCalls(const RowBlockContainer<unsigned>& data, const std::vector<feaid_t>& keys,
@@ -75,6 +85,7 @@ class SGDLearner : public Learner {
   Loss* loss_ = nullptr;
   SGDLearnerParam param_;
   std::vector<EpochCallback> epoch_end_callback_;
+  std::vector<std::shared_ptr<GpuEngine>> shard_engines_;     // GPUs 1..N-1 (num_gpus > 1)
 };
 
 }  // namespace difacto

@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <fstream>
+#include <thread>
 
 namespace difacto {
 
@@ -34,30 +35,68 @@ KWArgs SGDLearner::Init(const KWArgs& kwargs) {
   loss_ = Loss::Create(param_.loss, 2);
   static_cast<GpuFMLoss*>(loss_)->AttachEngine(updater->engine());
   remain = loss_->Init(remain);
+  if (param_.num_gpus > 1) {
+    // one engine (= one shard of the model) per GPU, the same hyper-parameters everywhere; wire the mailboxes
+    if (param_.fused != 1) throw ParamError("num_gpus > 1 needs fused = 1 (raw blocks through the sharded store)");
+    if (param_.num_gpus > 8) throw ParamError("num_gpus must be <= 8");
+    for (int r = 1; r < param_.num_gpus; ++r) {
+      KWArgs kw;
+      for (const auto& kv : kwargs) if (kv.first != "device") kw.push_back(kv);
+      kw.push_back(std::make_pair("device", std::to_string(r)));
+      KWArgs engine_kw;     // only what dfb_create knows: drop the learner's keys (it would report them as unknown)
+      SGDLearnerParam tmp;
+      engine_kw = tmp.InitAllowUnknown(kw);
+      shard_engines_.push_back(std::make_shared<GpuEngine>(engine_kw));
+    }
+    const int N = param_.num_gpus;
+    const size_t max_rows = static_cast<size_t>(std::max(param_.batch_size, 65536));     // validation reads 65536-row chunks
+    const size_t max_nnz = param_.shard_max_nnz > 0 ? static_cast<size_t>(param_.shard_max_nnz) : max_rows * 256;
+    std::vector<void*> boxes(N, nullptr);
+    for (int r = 0; r < N; ++r) {
+      const auto& e = ShardEngine(r);
+      e->Check(dfb_shard_init(e->handle(), r, N, max_rows, max_nnz, 0, 0, nullptr), "dfb_shard_init");
+      e->Check(dfb_shard_export(e->handle(), &boxes[r], nullptr), "dfb_shard_export");
+    }
+    for (int r = 0; r < N; ++r) ShardEngine(r)->Check(dfb_shard_connect(ShardEngine(r)->handle(), boxes.data()), "dfb_shard_connect");
+  }
   return remain;
 }
 
 // SGDLearner::RunScheduler, sgd_learner.cc:31-68 (+ model_in / model_out, declared in
 // sgd_param.h:53-54 but never acted on by the reference: Job::kLoadModel/kSaveModel are not issued)
 void SGDLearner::RunScheduler() {
+  // num_gpus = N > 1: one snapshot per shard, <name>_part-<r> (the format of Updater::Save per shard)
+  auto shard_name = [&](const std::string& base, int r) { return param_.num_gpus > 1 ? base + "_part-" + std::to_string(r) : base; };
   if (!param_.model_in.empty()) {
-    std::ifstream fi(param_.model_in, std::ios::binary);
-    if (!fi) throw Error("failed to open model_in " + param_.model_in);
-    bool has_aux = false;
-    GetUpdater()->Load(&fi, &has_aux);
-    if (verbose) printf("Loaded model from %s (%s aux data)\n", param_.model_in.c_str(), has_aux ? "with" : "without");
+    for (int r = 0; r < param_.num_gpus; ++r) {
+      const std::string fn = shard_name(param_.model_in, r);
+      std::ifstream fi(fn, std::ios::binary);
+      if (!fi) throw Error("failed to open model_in " + fn);
+      std::string blob((std::istreambuf_iterator<char>(fi)), std::istreambuf_iterator<char>());
+      int aux = 0;
+      ShardEngine(r)->Check(dfb_restore(ShardEngine(r)->handle(), blob.data(), blob.size(), &aux), "dfb_restore");
+      if (verbose) printf("Loaded model from %s (%s aux data)\n", fn.c_str(), aux ? "with" : "without");
+    }
   }
   RunEpochs();
   if (!param_.model_out.empty()) {
-    std::ofstream fo(param_.model_out, std::ios::binary);
-    if (!fo) throw Error("failed to open model_out " + param_.model_out);
-    GetUpdater()->Save(true, &fo);
-    if (verbose) printf("Saved model to %s\n", param_.model_out.c_str());
+    for (int r = 0; r < param_.num_gpus; ++r) {
+      const std::string fn = shard_name(param_.model_out, r);
+      std::ofstream fo(fn, std::ios::binary);
+      if (!fo) throw Error("failed to open model_out " + fn);
+      size_t n = 0;
+      ShardEngine(r)->Check(dfb_snapshot_size(ShardEngine(r)->handle(), 1, &n), "dfb_snapshot_size");
+      std::string blob(n, '\0');
+      ShardEngine(r)->Check(dfb_snapshot(ShardEngine(r)->handle(), 1, &blob[0], n), "dfb_snapshot");
+      fo.write(blob.data(), static_cast<std::streamsize>(n));
+      if (verbose) printf("Saved model to %s\n", fn.c_str());
+    }
   }
 }
 
 sgd::Progress SGDLearner::Predict() {
   if (param_.model_in.empty()) throw Error("task=predict needs model_in");
+  if (param_.num_gpus > 1) throw Error("task=predict runs on one GPU (load one shard, or train with num_gpus=1)");
   std::ifstream fi(param_.model_in, std::ios::binary);
   if (!fi) throw Error("failed to open model_in " + param_.model_in);
   bool has_aux = false;
@@ -116,6 +155,7 @@ void SGDLearner::RunEpochs() {
 // SGDLearner::RunEpoch, sgd_learner.cc:70-111: n = NumWorkers * num_jobs_per_epoch file parts,
 // executed in order (the reference's LocalTracker runs them serially on one thread too)
 void SGDLearner::RunEpoch(int epoch, int job_type, sgd::Progress* prog) {
+  if (param_.num_gpus > 1) { RunEpochSharded(epoch, job_type, prog); return; }
   const int n = store_->NumWorkers() * param_.num_jobs_per_epoch;
   for (int i = 0; i < n; ++i) {
     sgd::Job job;
@@ -124,6 +164,93 @@ void SGDLearner::RunEpoch(int epoch, int job_type, sgd::Progress* prog) {
     IterateData(job, &p);
     prog->Merge(p);
   }
+}
+
+namespace {
+// the workers of a sharded epoch step together: a round ends when no worker has a batch left
+struct RoundBarrier {
+  explicit RoundBarrier(int n) : n_(n) {}
+  bool Sync(bool has_batch) {       // returns whether ANY worker has a batch in this round
+    std::unique_lock<std::mutex> lk(mu_);
+    have_ += has_batch ? 1 : 0;
+    if (++waiting_ == n_) {
+      any_ = have_ > 0; have_ = 0; waiting_ = 0; ++gen_;
+      cv_.notify_all();
+      return any_;
+    }
+    const unsigned long long g = gen_;
+    cv_.wait(lk, [&] { return gen_ != g; });
+    return any_;
+  }
+  int n_, waiting_ = 0, have_ = 0;
+  bool any_ = false;
+  unsigned long long gen_ = 0;
+  std::mutex mu_;
+  std::condition_variable cv_;
+};
+}  // namespace
+
+// num_gpus = N > 1: the epoch of sgd_learner.cc:70-111 with N workers in parallel.  File part i of the
+// N * num_jobs_per_epoch parts goes to worker i % N (the reference's tracker hands parts to whichever worker is
+// free; the assignment is fixed here so that runs are reproducible).  Every round each worker contributes its next
+// minibatch (or an empty one when its parts are exhausted) to ONE collective sharded step.
+void SGDLearner::RunEpochSharded(int epoch, int job_type, sgd::Progress* prog) {
+  const int N = param_.num_gpus;
+  const int nparts = N * param_.num_jobs_per_epoch;
+  const bool train = job_type == sgd::Job::kTraining;
+  const bool push_cnt = train && epoch == 0;      // sgd_learner.cc:201-202
+  RoundBarrier barrier(N);
+  std::vector<sgd::Progress> progs(N);
+  std::vector<std::string> errors(N);
+  auto worker = [&](int r) {
+    try {
+      const auto& eng = ShardEngine(r);
+      int part = r;
+      std::unique_ptr<BatchReader> reader;
+      auto next = [&]() -> bool {
+        for (;;) {
+          if (!reader) {
+            if (part >= nparts) return false;
+            reader.reset(new BatchReader(train ? param_.data_in : param_.data_val, param_.data_format,
+                                         static_cast<unsigned>(part), static_cast<unsigned>(nparts),
+                                         train ? static_cast<unsigned>(param_.batch_size) : 65536u,
+                                         train ? static_cast<unsigned>(param_.batch_size) * static_cast<unsigned>(param_.shuffle) : 0u,
+                                         train ? param_.neg_sampling : 1.0f, static_cast<unsigned>(epoch)));
+          }
+          if (reader->Next()) return true;
+          reader.reset();
+          part += N;
+        }
+      };
+      for (;;) {
+        bool has = false;
+        if (errors[r].empty()) {
+          try { has = next(); } catch (const std::exception& e) { errors[r] = e.what(); }
+        }
+        if (!barrier.Sync(has)) break;
+        dfb_progress pr;
+        if (has) {
+          const auto blk = reader->Value();
+          eng->Check(dfb_shard_step_async(eng->handle(), blk.size, reinterpret_cast<const uint64_t*>(blk.offset), blk.index,
+                                          blk.value, blk.label, push_cnt ? 1 : 0, train ? 1 : 0), "dfb_shard_step_async");
+        } else {
+          eng->Check(dfb_shard_step_async(eng->handle(), 0, nullptr, nullptr, nullptr, nullptr, push_cnt ? 1 : 0, train ? 1 : 0),
+                     "dfb_shard_step_async");
+        }
+        eng->Check(dfb_wait_step(eng->handle(), &pr), "dfb_wait_step");
+        progs[r].loss += pr.loss; progs[r].penalty += pr.penalty; progs[r].auc += pr.auc; progs[r].nrows += pr.nrows;
+      }
+    } catch (const std::exception& e) {
+      errors[r] = e.what();
+      // leave the collective cleanly: the other workers would wait for this one's step counters only until
+      // shard_timeout_ms, then report DFB_ERR_TIMEOUT themselves
+    }
+  };
+  std::vector<std::thread> th;
+  for (int r = 0; r < N; ++r) th.emplace_back(worker, r);
+  for (auto& t : th) t.join();
+  for (int r = 0; r < N; ++r) if (!errors[r].empty()) throw Error("worker " + std::to_string(r) + ": " + errors[r]);
+  for (int r = 0; r < N; ++r) prog->Merge(progs[r]);
 }
 
 // SGDLearner::GetPos, sgd_learner.cc:113-127

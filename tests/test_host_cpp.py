@@ -226,3 +226,53 @@ def test_cli_task_predict(host_bin, libsvm_fixture, tmp_path, rcv1):
     assert np.allclose(got, ref, rtol=2e-3, atol=2e-3)
     loss = float(out.stdout.split("loss = ")[1].split(",")[0])
     assert abs(loss - O.evaluate(rcv1["label"], ref)) <= 2e-3 * abs(loss) + 1e-2
+
+
+def _synthetic_libsvm(path, rows, seed):
+    rng = np.random.default_rng(seed)
+    w = rng.normal(0, 1, 400)
+    with open(path, "w") as f:
+        for _ in range(rows):
+            ids = np.unique(rng.integers(1, 400, rng.integers(5, 25)))
+            x = rng.random(len(ids)).astype(np.float32)
+            y = 1 if (w[ids] * x).sum() + rng.normal(0, 0.3) > 0 else -1
+            f.write(f"{y} " + " ".join(f"{int(i) * 7919}:{float(v):.6g}" for i, v in zip(ids, x)) + "\n")
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_sharded_store(host_bin, tmp_path):
+    """num_gpus=2: the C++ learner drives the NVLink-sharded store (dfb_shard_*) with one worker thread per GPU,
+    the worker/server split SGDLearner::RunEpoch was written for (sgd_learner.cc:78-89).  The run must learn like the
+    one-GPU run (same data, same hyper-parameters; batch composition per step differs), save one snapshot per shard,
+    and a reloaded model must reproduce the validation loss it was saved with."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    exe = os.path.join(host_bin, "difacto_b200")
+    data, val = str(tmp_path / "train.libsvm"), str(tmp_path / "val.libsvm")
+    _synthetic_libsvm(data, 4000, 1)
+    _synthetic_libsvm(val, 1000, 2)
+    common = [f"data_in={data}", f"data_val={val}", "V_dim=16", "l1=0.01", "l2=0.01", "lr=0.1", "V_lr=0.05", "V_threshold=2",
+              "batch_size=200", "shuffle=0", "num_jobs_per_epoch=1", "max_num_epochs=4", "stop_rel_objv=0", "stop_val_auc=-1e9",
+              "table_capacity=65536"]
+
+    def losses(out, tag):
+        return [float(l.split("loss = ")[1].split(",")[0]) for l in out.stdout.split("\n") if f"{tag}: loss" in l]
+
+    one = subprocess.run([exe] + common, capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0, one.stderr[-2000:]
+    model = str(tmp_path / "model")
+    two = subprocess.run([exe] + common + ["num_gpus=2", f"model_out={model}"], capture_output=True, text=True, timeout=300)
+    assert two.returncode == 0, two.stderr[-2000:]
+    t1, t2, v1, v2 = losses(one, "Training"), losses(two, "Training"), losses(one, "Validation"), losses(two, "Validation")
+    assert len(t2) == 4 and len(v2) == 4
+    assert t2[0] == pytest.approx(t1[0], rel=1e-5)                 # epoch 0 starts from w = 0 on the same rows: 4000 * log 2 ...
+    assert all(b < a for a, b in zip(t2[:-1], t2[1:]))             # ... and then learns
+    assert v2[-1] == pytest.approx(v1[-1], rel=0.05)               # like the one-GPU run (two half-size streams of batches)
+    assert os.path.exists(model + "_part-0") and os.path.exists(model + "_part-1")
+    again = subprocess.run([exe] + [c for c in common if not c.startswith("max_num_epochs")] +
+                           ["num_gpus=2", f"model_in={model}", "max_num_epochs=1", "lr=1e-30", "V_lr=1e-30"],
+                           capture_output=True, text=True, timeout=300)
+    assert again.returncode == 0, again.stderr[-2000:]
+    # lr ~ 0: the reloaded model does not move, so its validation loss is the one it was saved with
+    assert losses(again, "Validation")[0] == pytest.approx(v2[-1], rel=1e-4)
