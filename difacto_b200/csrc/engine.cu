@@ -77,8 +77,11 @@ int check_dev_err(dfb_engine* h) {
     case DFB_ERR_INVALID:
       return h->fail(code, "invalid input detected on device (a CHECK of the reference would have failed: "
                            "lens[i] != V_dim+1, gradient for a key without V, or key == UINT64_MAX)");
+    case DFB_ERR_TIMEOUT:
+      return h->fail(code, "a rank of the sharded store did not reach this step within shard_timeout_ms (peer crashed, ran out "
+                           "of data without calling the step with nrows = 0, or the ranks' hosts deadlocked)");
     default:
-      return h->fail(code, "device-side error");
+      return h->fail(code, "device-side error " + std::to_string(code));
   }
 }
 
@@ -1146,7 +1149,8 @@ int dfbh::stage_raw(dfb_engine* h, dfb_engine::InSet& in, size_t nrows, size_t n
                     const uint64_t* ids, const float* value, const float* label) {
   cudaStream_t cs = h->copy_stream;
   if (h->seq >= 2) DFB_CUDA(h, cudaStreamWaitEvent(cs, in.consumed, 0));
-  DFB_TRY(h2d(h, in.off, offset, (nrows + 1) * sizeof(uint64_t), cs));
+  if (nrows) DFB_TRY(h2d(h, in.off, offset, (nrows + 1) * sizeof(uint64_t), cs));     // an empty batch has no offset array
+  else DFB_TRY(h->ensure(in.off, 16));
   DFB_TRY(h2d(h, in.ids, ids, nnz * sizeof(uint64_t), cs));
   if (value) DFB_TRY(h2d(h, in.val, value, nnz * sizeof(float), cs));
   DFB_TRY(h2d(h, in.lab, label, nrows * sizeof(float), cs));

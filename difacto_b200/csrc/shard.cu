@@ -411,6 +411,27 @@ int dfb_shard_init(dfb_handle h, int rank, int nranks, size_t max_rows, size_t m
       (rc = h->ensure(sh->ws, (tot / 32 + 64) * 4)))
     return fail(rc);
   if (nranks > 1 && ((rc = h->ensure(sh->conf, tot)) || (rc = h->ensure(sh->vsave, tot * (size_t)K * 4)))) return fail(rc);
+  // Every workspace a step can touch is allocated NOW, for the declared capacities: a cudaMalloc / cudaFree in the
+  // middle of a step is not just slow -- with peer access enabled it synchronises the peer devices, whose pollers
+  // may be waiting for the very step this rank has not finished enqueuing (ranks that are threads of one process).
+  {
+    const size_t n1 = max_nnz, B = max_rows;
+    DevBuf* nnz8[] = {&h->l_rkeys, &h->l_skeys, &sh->L.keys, &sh->L.occ_sorted};
+    DevBuf* nnz4[] = {&h->l_pos, &h->l_spos, &h->l_head, &h->l_rank, &h->l_nnzrow, &sh->L.lidx, &sh->L.cnt, &sh->L.col_end};
+    for (auto* b : nnz8) if ((rc = h->ensure(*b, n1 * 8))) return fail(rc);
+    for (auto* b : nnz4) if ((rc = h->ensure(*b, n1 * 4))) return fail(rc);
+    HotWs hws;
+    if ((rc = h->ensure(sh->L.col_start, (n1 + 1) * 4)) || (rc = h->ensure(sh->L.scal, 16)) ||
+        (rc = h->ensure(h->l_tmp, localize_sort_tmp_bytes(n1))) || (rc = h->ensure(sh->rowcnt, (size_t)nranks * (B + 1) * 4)) ||
+        (rc = h->ensure(sh->pred[0], B * 4)) || (rc = h->ensure(sh->pred[1], B * 4)) || (rc = h->ensure(h->auc_k, B * 4)) ||
+        (rc = h->ensure(h->auc_v, B * 4)) || (rc = h->ensure(h->auc_tmp, sort_tmp_bytes(B))) ||
+        (rc = dfbh::hot_ws(h, Kseg, Nseg, &hws)))
+      return fail(rc);
+    for (auto& in : h->in)
+      if ((rc = h->ensure(in.off, (B + 1) * 8)) || (rc = h->ensure(in.ids, n1 * 8)) || (rc = h->ensure(in.val, n1 * 4)) ||
+          (rc = h->ensure(in.lab, B * 4)))
+        return fail(rc);
+  }
   const size_t np = (size_t)nranks + 4;
   if ((e = cudaMalloc(&sh->dprog, np * sizeof(DevProgress))) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMalloc"));
   if ((e = cudaMemset(sh->dprog, 0, np * sizeof(DevProgress))) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMemset"));
