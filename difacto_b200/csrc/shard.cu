@@ -461,11 +461,17 @@ int dfb_shard_connect(dfb_handle h, void* const* peer_mailbox) {
     if (!peer_mailbox[s]) return h->fail(DFB_ERR_INVALID, "peer mailbox pointer is NULL");
     sh.peer[s] = peer_mailbox[s];
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, peer_mailbox[s]) == cudaSuccess && at.device != h->device) {
+    cudaError_t pe = cudaPointerGetAttributes(&at, peer_mailbox[s]);
+    if (pe != cudaSuccess) return h->cuda_fail(pe, "cudaPointerGetAttributes(peer mailbox)");
+    if (at.type != cudaMemoryTypeDevice) return h->fail(DFB_ERR_INVALID, "peer mailbox is not device memory");
+    if (at.device != h->device) {
+      int can = 0;
+      DFB_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, at.device));
+      if (!can) return h->fail(DFB_ERR_INVALID, "this GPU cannot access the peer GPU's memory");
       cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);     // same-process peers; IPC mappings enabled it already
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return h->cuda_fail(e, "cudaDeviceEnablePeerAccess");
+      cudaGetLastError();
     }
-    cudaGetLastError();
   }
   sh.connected = true;
   return DFB_OK;

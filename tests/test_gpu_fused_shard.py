@@ -166,6 +166,35 @@ def test_fused_shard_segment_capacity_is_reported():
     assert ei.value.code == capi.DFB_ERR_CAPACITY
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("big", [False, True])
+def test_fused_shard_two_gpus_one_process_vs_oracle_simulation(big):
+    """two engines on two devices inside ONE process (peer access instead of CUDA IPC; the C++ CLI's num_gpus mode):
+    one host thread, monolithic steps (the devices have their own hardware queues); big = the CLI's default capacities"""
+    from difacto_b200.sharded import FusedShardedStore
+    S = 2
+    engines = [capi.Engine(device=r, table_capacity=1 << 14, shard_timeout_ms=8000, **KW) for r in range(S)]
+    if big:
+        FusedShardedStore.connect_local(engines, max_rows=65536, max_nnz=65536 * 64)
+    else:
+        FusedShardedStore.connect_local(engines, max_rows=128, max_nnz=4096)
+    prog = [[] for _ in range(S)]
+    for step in range(STEPS):
+        for r in range(S):
+            off, idx, val, lab = batch_fn(r, step)
+            engines[r].shard_step_async(len(lab), off, idx, val, lab, push_cnt=step < 2, is_train=True)
+        for r in range(S):
+            prog[r].append(engines[r].wait_step())
+    shards, workers, per_step = simulate(S, STEPS, KW, batch_fn)
+    for step in range(STEPS):
+        for r in range(S):
+            check_progress(prog[r][step], per_step[step][r], f"step {step} worker {r}")
+    keys = all_keys(S, STEPS, batch_fn)
+    own = key_owner_np(keys, S)
+    for s in range(S):
+        check_shard(engines[s], shards[s], keys[own == s], f"shard {s}")
+
+
 # ---------------------------------------------------------------------------------------------------------
 # one process per GPU, mailboxes shared through CUDA IPC
 # ---------------------------------------------------------------------------------------------------------
