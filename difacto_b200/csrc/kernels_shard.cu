@@ -93,7 +93,10 @@ __global__ void k_shard_bounds(const uint64_t* __restrict__ keys, const unsigned
   *wb = b;
 }
 
-// keys, column offsets and column payload of every owner's segment -> that owner's mailbox
+// keys, column offsets and column payload of every owner's segment -> that owner's mailbox.
+// On the wire every minibatch is VALUED ((row << 32) | bits(x) per occurrence, x = 1 for a binary batch): an owner
+// consumes the slices of all workers with one kernel flavour, whatever mix of binary and valued batches (or empty
+// ones) the workers happen to hold in a step.
 template <bool HAS_VAL>
 __global__ void __launch_bounds__(256) k_shard_scatter(ScatterArgs a) {
   __shared__ ShardBounds b;
@@ -119,8 +122,9 @@ __global__ void __launch_bounds__(256) k_shard_scatter(ScatterArgs a) {
     int s = 0;
     while ((int)j >= b.nb[s + 1]) ++s;
     const unsigned r = j - (unsigned)b.nb[s];
-    if (HAS_VAL) reinterpret_cast<unsigned long long*>(a.occ_dst[s])[r] = reinterpret_cast<const unsigned long long*>(a.occ)[j];
-    else reinterpret_cast<uint32_t*>(a.occ_dst[s])[r] = reinterpret_cast<const uint32_t*>(a.occ)[j];
+    reinterpret_cast<unsigned long long*>(a.occ_dst[s])[r] =
+        HAS_VAL ? reinterpret_cast<const unsigned long long*>(a.occ)[j]
+                : (((unsigned long long)reinterpret_cast<const uint32_t*>(a.occ)[j] << 32) | 0x3f800000ULL);
   }
   if (blockIdx.x == 0 && threadIdx.x < (unsigned)S) {
     const int s = threadIdx.x;
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(256) k_shard_fill(const uint64_t* __restrict__
       if (own < 8) {
         const int at = s_pos[wid][own] + __popc(peers & ((1u << lane) - 1u));
         d.ridx_dst[own][at] = u - (uint32_t)b.kb[own];
-        if (HAS_VAL) d.rval_dst[own][at] = x;
+        d.rval_dst[own][at] = HAS_VAL ? x : 1.f;
       }
       __syncwarp();
       if (own < 8 && lane == __ffs(peers) - 1) s_pos[wid][own] += __popc(peers);

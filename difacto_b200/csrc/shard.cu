@@ -20,7 +20,10 @@
 // parity.  Dependencies on the SAME GPU are CUDA events, dependencies on other GPUs are step counters in
 // peer memory polled by one-warp kernels (with a timeout), so the FIFO order of the host's enqueues is
 // deadlock-free whatever the stream-to-hardware-queue mapping is.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "engine_internal.cuh"
 #include "shard_layout.cuh"
@@ -62,6 +65,20 @@ struct ShardState {
 };
 
 namespace {
+
+// DFB_DEBUG_SYNC=1: synchronise the device after every launch group of a sharded step and name the first one that
+// faulted (debugging aid; the ranks still only wait for work that is already enqueued, see shard_phase)
+bool dbg_on() {
+  static const bool on = getenv("DFB_DEBUG_SYNC") != nullptr;
+  return on;
+}
+#define DFB_DBG(h, tag)                                                                            \
+  do {                                                                                             \
+    if (dbg_on()) {                                                                                \
+      cudaError_t _e = cudaDeviceSynchronize();                                                    \
+      if (_e != cudaSuccess) return (h)->cuda_fail(_e, "sharded step, after " tag);                 \
+    }                                                                                              \
+  } while (0)
 
 int shard_begin(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, const uint64_t* d_ids,
                 const float* d_val, const float* d_lab, int push_cnt, int is_train, cudaEvent_t inputs_ready,
@@ -105,7 +122,7 @@ int shard_phase(dfb_engine* h, int phase) {
   const uint64_t t = sh.step;
   const int d = (int)(t & 1);
   const unsigned long long fv = t + 1;
-  const bool valued = d_val != nullptr;
+  const bool valued = d_val != nullptr;      // of THIS rank's batch; on the wire every batch is valued (kernels_shard.cu)
   const unsigned remote = ((1u << S) - 1u) & ~(1u << me);
   cudaStream_t W = sh.w_stream, O = h->stream, A = h->aux_stream, F = sh.f_stream;
   void* mine = sh.mailbox;
@@ -129,6 +146,7 @@ int shard_phase(dfb_engine* h, int phase) {
     StageTimer tm(h, 5, W);
     DFB_TRY(dfbh::localize_dev(h, nrows, nnz, d_off, d_ids, d_val, ~0ULL, sh.L, W, false, false, &Ucap));   // Localizer(-1), sgd_learner.cc:203
   }
+  DFB_DBG(h, "localize");
   StageTimer tm_slice(h, 6, W);
   ShardBounds* wb = sh.wb.as<ShardBounds>();
   h->launches += launch_shard_bounds(sh.L.keys.as<uint64_t>(), sh.L.dU(), Ucap, sh.L.col_start.as<int>(), nnz, S, Kseg,
@@ -153,9 +171,12 @@ int shard_phase(dfb_engine* h, int phase) {
       fd.ridx_dst[s] = lay.at<uint32_t>(sh.peer[s], lay.off_ridx, lay.str_ridx, d, me);
       fd.rval_dst[s] = lay.at<float>(sh.peer[s], lay.off_rval, lay.str_rval, d, me);
     }
+    DFB_DBG(h, "bounds");
     h->launches += launch_shard_scatter(a, valued, nnz ? nnz : 1, W);
+    DFB_DBG(h, "scatter");
     h->launches += launch_shard_subcsr(d_off, sh.L.lidx.as<uint32_t>(), d_val, nrows, wb, S, sh.rowcnt.as<int>(), rd, fd, W);
   }
+  DFB_DBG(h, "subcsr");
   tm_slice.stop();
   {
     SignalDst sd;
@@ -184,6 +205,7 @@ int shard_phase(dfb_engine* h, int phase) {
   for (int r = 0; r < S; ++r)
     h->launches += launch_shard_lookup(h->tab, la, r, is_train || push_cnt, sh.conf.as<unsigned char>(),
                                        sh.vsave.as<float>(), K, O);
+  DFB_DBG(h, "lookup");
   if (push_cnt) {
     // Push(kFeaCount) before Pull (sgd_learner.cc:214-217): one Update per worker, rank order
     for (int r = 0; r < S; ++r)
@@ -194,6 +216,7 @@ int shard_phase(dfb_engine* h, int phase) {
                                       la.vrow + (size_t)r * Kseg, la.wv + (size_t)r * Kseg, O);
     if (la.stamp) h->launches += launch_shard_save_conf(h->tab, la, sh.conf.as<unsigned char>(), sh.vsave.as<float>(), K, O);
   }
+  DFB_DBG(h, "feacnt / pull view");
   {
     PartArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -201,7 +224,7 @@ int shard_phase(dfb_engine* h, int phase) {
     for (int r = 0; r < S; ++r) {
       pa.s[r].rowptr = lay.at<uint64_t>(mine, lay.off_rowptr, lay.str_rowptr, d, r);
       pa.s[r].ridx = lay.at<uint32_t>(mine, lay.off_ridx, lay.str_ridx, d, r);
-      pa.s[r].rval = valued ? lay.at<float>(mine, lay.off_rval, lay.str_rval, d, r) : nullptr;
+      pa.s[r].rval = lay.at<float>(mine, lay.off_rval, lay.str_rval, d, r);
       pa.s[r].wv = la.wv + (size_t)r * Kseg;
       pa.s[r].hdr = hdr[r];
       pa.s[r].out_xv = lay.at<float>(sh.peer[r], lay.off_part_xv, lay.str_part_xv, d, me);
@@ -210,10 +233,11 @@ int shard_phase(dfb_engine* h, int phase) {
     FmView v;
     memset(&v, 0, sizeof(v));
     v.vbase = h->tab.V; v.vstride = h->tab.rs; v.l2hint = h->l2_hints;
-    int nl = launch_fm_partial(K, valued, v, pa, O);
+    int nl = launch_fm_partial(K, true, v, pa, O);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
     h->launches += nl;
   }
+  DFB_DBG(h, "partial sums");
   tm_fwd.stop();
   {
     SignalDst sd;
@@ -244,6 +268,7 @@ int shard_phase(dfb_engine* h, int phase) {
     int nl = launch_shard_reduce(K, ra, W);
     if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
     h->launches += nl;
+    DFB_DBG(h, "reduce");
   }
   {
     SignalDst sd;
@@ -269,9 +294,11 @@ int shard_phase(dfb_engine* h, int phase) {
   StageTimer tm_upd(h, 9, O);
   // the InitV requests of all workers' updates: flags[S][Kseg], zero where no key is (one pass after the last update)
   if (is_train) DFB_CUDA(h, cudaMemsetAsync(flags, 0, (size_t)S * Kseg * sizeof(int), O));
+  DFB_DBG(h, "flags memset");
   for (int r = 0; r < S; ++r) {
     if (r == me) DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_reduce[d], 0));
     else h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_PXV, r), 8, 1u, fv, sh.timeout_cycles, h->tab.prog, O);
+    DFB_DBG(h, "wait for a worker's p*XV");
     const size_t o = (size_t)r * Kseg;
     const int* cstart = lay.at<int>(mine, lay.off_cstart, lay.str_cstart, d, r);
     if (is_train) {
@@ -287,22 +314,26 @@ int shard_phase(dfb_engine* h, int phase) {
       HotWs hws;
       HotPart hp;
       DFB_TRY(dfbh::hot_ws(h, Kseg, lay.Nseg, &hws));
-      h->launches += launch_hot_prereduce(K, Kseg, &hdr[r]->nkeys, cstart, cstart + 1, occ_r, valued, p_r, pxv_r,
+      h->launches += launch_hot_prereduce(K, Kseg, &hdr[r]->nkeys, cstart, cstart + 1, occ_r, true, p_r, pxv_r,
                                           h->hot_split, hws, &hp, O);
+      DFB_DBG(h, "hot-key pre-reduction");
       int nl = launch_bwd_update(tt, h->prm, la.slot + o, la.vrow + o, Kseg, &hdr[r]->nkeys, cstart, cstart + 1,
-                                 occ_r, valued, p_r, pxv_r, flags + o, 1, &ap, hp.part ? &hp : nullptr, O);
+                                 occ_r, true, p_r, pxv_r, flags + o, 1, &ap, hp.part ? &hp : nullptr, O);
       if (nl < 0) return h->fail(DFB_ERR_INVALID, "unsupported V_dim for the sharded store");
       h->launches += nl;
     } else {
       h->launches += launch_penalty(h->prm, sh.src_prog(r), la.w + o, la.vrow + o, h->tab.V, h->tab.rs, 0, Kseg,
                                     &hdr[r]->nkeys, O);
     }
+    DFB_DBG(h, "update of one worker");
     h->launches += launch_shard_done(sh.src_prog(r), h->tab.prog, lay.at<double>(sh.peer[r], lay.off_pen, lay.str_pen, d, me),
                                      lay.flag(sh.peer[r], ShardLayout::F_DONE, me), fv, O);
+    DFB_DBG(h, "done signal");
   }
   // InitV (sgd_updater.cc:121-126,140-147) for the keys whose w left zero, in worker-major key order -- the order in
   // which the reference's server would have met them
   if (is_train) h->launches += launch_initv(h->tab, h->prm, la.slot, (size_t)S * Kseg, nullptr, flags, ws, O);
+  DFB_DBG(h, "InitV");
   tm_upd.stop();
   DFB_CUDA(h, cudaEventRecord(sh.ev_upd[d], O));
   }
@@ -313,6 +344,7 @@ int shard_phase(dfb_engine* h, int phase) {
   if (auc) DFB_CUDA(h, cudaStreamWaitEvent(F, sh.ev_auc[d], 0));
   DFB_CUDA(h, cudaStreamWaitEvent(F, sh.ev_upd[d], 0));
   h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_DONE, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, F);
+  DFB_DBG(h, "done flags");
   h->launches += launch_shard_collect(lay.at<double>(mine, lay.off_pen, lay.str_pen, d, 0), (int)(lay.str_pen / 8), S,
                                       sh.prog_w(d), h->tab.prog, sh.stage(d), F);
   if (h->submitted - h->collected == (uint64_t)dfb_engine::kRing) DFB_TRY(dfbh::collect_one(h, &h->backlog));
@@ -437,6 +469,8 @@ int dfb_shard_init(dfb_handle h, int rank, int nranks, size_t max_rows, size_t m
   if ((e = cudaMemset(sh->dprog, 0, np * sizeof(DevProgress))) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMemset"));
   sh->connected = nranks == 1;
   if (mailbox_bytes) *mailbox_bytes = sh->lay.total;
+  // cudaMemset of device memory is asynchronous: the zeroed mailbox must be in place before any peer may store into it
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(h->cuda_fail(e, "cudaDeviceSynchronize"));
   return DFB_OK;
 }
 
@@ -474,6 +508,7 @@ int dfb_shard_connect(dfb_handle h, void* const* peer_mailbox) {
     }
   }
   sh.connected = true;
+  DFB_CUDA(h, cudaDeviceSynchronize());
   return DFB_OK;
 }
 

@@ -8,8 +8,9 @@
 //   fused = 0: the reference's own sequence of plugin calls Store::Pull -> GetPos -> Loss::Predict ->
 //              Evaluate -> penalty -> AUC -> Loss::CalcGrad -> Store::Push through the adapter classes.
 // num_gpus = N > 1 (with fused = 1): the worker/server split SGDLearner::RunEpoch was written for
-// (sgd_learner.cc:78-89): N worker threads, each reading its own file parts and owning GPU r's shard of the
-// model, one collective dfb_shard_step_async per round of minibatches (the NVLink-sharded store, csrc/shard.cu).
+// (sgd_learner.cc:78-89): N workers, each reading its own file parts (parsed on helper threads) and owning GPU
+// r's shard of the model, one collective sharded step per round of minibatches, enqueued by one host thread in
+// interleaved phases (dfb_shard_begin_async + dfb_shard_phase; the NVLink-sharded store, csrc/shard.cu).
 #pragma once
 #include <cmath>
 #include <condition_variable>
@@ -72,6 +73,7 @@ class SGDLearner : public Learner {
   void IterateData(const sgd::Job& job, sgd::Progress* prog);
   /** num_gpus > 1: one epoch over all N * num_jobs_per_epoch file parts, part i handled by worker i % N */
   void RunEpochSharded(int epoch, int job_type, sgd::Progress* prog);
+  void LoadShards();
   /** engine of GPU r (r = 0: the updater's own) */
   const std::shared_ptr<GpuEngine>& ShardEngine(int r) { return r == 0 ? GetUpdater()->engine() : shard_engines_[r - 1]; }
   void BatchFused(const RowBlockContainer<unsigned>& data, const std::vector<feaid_t>& keys,

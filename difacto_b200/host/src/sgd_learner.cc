@@ -55,11 +55,25 @@ KWArgs SGDLearner::Init(const KWArgs& kwargs) {
     for (int r = 0; r < N; ++r) {
       const auto& e = ShardEngine(r);
       e->Check(dfb_shard_init(e->handle(), r, N, max_rows, max_nnz, 0, 0, nullptr), "dfb_shard_init");
-      e->Check(dfb_shard_export(e->handle(), &boxes[r], nullptr), "dfb_shard_export");
+      unsigned char ipc_handle[64];      // unused here (same process); other processes would open it with dfb_peer_open
+      e->Check(dfb_shard_export(e->handle(), &boxes[r], getenv("DFB_NO_IPC_EXPORT") ? nullptr : ipc_handle), "dfb_shard_export");
     }
     for (int r = 0; r < N; ++r) ShardEngine(r)->Check(dfb_shard_connect(ShardEngine(r)->handle(), boxes.data()), "dfb_shard_connect");
   }
   return remain;
+}
+
+// model_in -> the engine(s): one file, or <name>_part-<r> per shard when num_gpus = N > 1
+void SGDLearner::LoadShards() {
+  for (int r = 0; r < param_.num_gpus; ++r) {
+    const std::string fn = param_.num_gpus > 1 ? param_.model_in + "_part-" + std::to_string(r) : param_.model_in;
+    std::ifstream fi(fn, std::ios::binary);
+    if (!fi) throw Error("failed to open model_in " + fn);
+    std::string blob((std::istreambuf_iterator<char>(fi)), std::istreambuf_iterator<char>());
+    int aux = 0;
+    ShardEngine(r)->Check(dfb_restore(ShardEngine(r)->handle(), blob.data(), blob.size(), &aux), "dfb_restore");
+    if (verbose) printf("Loaded model from %s (%s aux data)\n", fn.c_str(), aux ? "with" : "without");
+  }
 }
 
 // SGDLearner::RunScheduler, sgd_learner.cc:31-68 (+ model_in / model_out, declared in
@@ -67,17 +81,7 @@ KWArgs SGDLearner::Init(const KWArgs& kwargs) {
 void SGDLearner::RunScheduler() {
   // num_gpus = N > 1: one snapshot per shard, <name>_part-<r> (the format of Updater::Save per shard)
   auto shard_name = [&](const std::string& base, int r) { return param_.num_gpus > 1 ? base + "_part-" + std::to_string(r) : base; };
-  if (!param_.model_in.empty()) {
-    for (int r = 0; r < param_.num_gpus; ++r) {
-      const std::string fn = shard_name(param_.model_in, r);
-      std::ifstream fi(fn, std::ios::binary);
-      if (!fi) throw Error("failed to open model_in " + fn);
-      std::string blob((std::istreambuf_iterator<char>(fi)), std::istreambuf_iterator<char>());
-      int aux = 0;
-      ShardEngine(r)->Check(dfb_restore(ShardEngine(r)->handle(), blob.data(), blob.size(), &aux), "dfb_restore");
-      if (verbose) printf("Loaded model from %s (%s aux data)\n", fn.c_str(), aux ? "with" : "without");
-    }
-  }
+  if (!param_.model_in.empty()) LoadShards();
   RunEpochs();
   if (!param_.model_out.empty()) {
     for (int r = 0; r < param_.num_gpus; ++r) {
@@ -96,7 +100,17 @@ void SGDLearner::RunScheduler() {
 
 sgd::Progress SGDLearner::Predict() {
   if (param_.model_in.empty()) throw Error("task=predict needs model_in");
-  if (param_.num_gpus > 1) throw Error("task=predict runs on one GPU (load one shard, or train with num_gpus=1)");
+  if (param_.num_gpus > 1) {
+    // the shards of a num_gpus = N run, scored by the same N GPUs (loss / AUC only: the rows of a step are spread
+    // over the workers, so there is no single prediction file to write)
+    if (!param_.pred_out.empty()) throw Error("pred_out needs num_gpus=1 (the predictions of a sharded run are spread over the workers)");
+    LoadShards();
+    sgd::Progress prog;
+    param_.data_val = param_.data_in;
+    RunEpochSharded(0, sgd::Job::kValidation, &prog);
+    if (verbose) printf(" - Prediction: %s, rows = %g\n", prog.TextString().c_str(), prog.nrows);
+    return prog;
+  }
   std::ifstream fi(param_.model_in, std::ios::binary);
   if (!fi) throw Error("failed to open model_in " + param_.model_in);
   bool has_aux = false;
@@ -166,91 +180,77 @@ void SGDLearner::RunEpoch(int epoch, int job_type, sgd::Progress* prog) {
   }
 }
 
-namespace {
-// the workers of a sharded epoch step together: a round ends when no worker has a batch left
-struct RoundBarrier {
-  explicit RoundBarrier(int n) : n_(n) {}
-  bool Sync(bool has_batch) {       // returns whether ANY worker has a batch in this round
-    std::unique_lock<std::mutex> lk(mu_);
-    have_ += has_batch ? 1 : 0;
-    if (++waiting_ == n_) {
-      any_ = have_ > 0; have_ = 0; waiting_ = 0; ++gen_;
-      cv_.notify_all();
-      return any_;
-    }
-    const unsigned long long g = gen_;
-    cv_.wait(lk, [&] { return gen_ != g; });
-    return any_;
-  }
-  int n_, waiting_ = 0, have_ = 0;
-  bool any_ = false;
-  unsigned long long gen_ = 0;
-  std::mutex mu_;
-  std::condition_variable cv_;
-};
-}  // namespace
-
-// num_gpus = N > 1: the epoch of sgd_learner.cc:70-111 with N workers in parallel.  File part i of the
-// N * num_jobs_per_epoch parts goes to worker i % N (the reference's tracker hands parts to whichever worker is
-// free; the assignment is fixed here so that runs are reproducible).  Every round each worker contributes its next
-// minibatch (or an empty one when its parts are exhausted) to ONE collective sharded step.
+// num_gpus = N > 1: the epoch of sgd_learner.cc:70-111 with N workers.  File part i of the N * num_jobs_per_epoch
+// parts goes to worker i % N (the reference's tracker hands parts to whichever worker is free; the assignment is fixed
+// here so that runs are reproducible).  Every round each worker contributes its next minibatch (or an empty one when
+// its parts are exhausted) to ONE collective sharded step.  One host thread drives all N engines and interleaves
+// the five enqueue phases of the step (dfb_shard_begin_async + dfb_shard_phase): nothing in a step waits for
+// the host, so the GPUs run concurrently; the readers parse their next batches on helper threads meanwhile.
 void SGDLearner::RunEpochSharded(int epoch, int job_type, sgd::Progress* prog) {
   const int N = param_.num_gpus;
   const int nparts = N * param_.num_jobs_per_epoch;
   const bool train = job_type == sgd::Job::kTraining;
   const bool push_cnt = train && epoch == 0;      // sgd_learner.cc:201-202
-  RoundBarrier barrier(N);
-  std::vector<sgd::Progress> progs(N);
-  std::vector<std::string> errors(N);
-  auto worker = [&](int r) {
+  struct Worker {
+    int part = 0;
+    std::unique_ptr<BatchReader> reader;
+    bool has = false;
+    std::string error;
+  };
+  std::vector<Worker> w(N);
+  for (int r = 0; r < N; ++r) w[r].part = r;
+  auto next = [&](int r) {          // host only (file parsing): runs on a helper thread per worker
+    Worker& me = w[r];
+    me.has = false;
     try {
-      const auto& eng = ShardEngine(r);
-      int part = r;
-      std::unique_ptr<BatchReader> reader;
-      auto next = [&]() -> bool {
-        for (;;) {
-          if (!reader) {
-            if (part >= nparts) return false;
-            reader.reset(new BatchReader(train ? param_.data_in : param_.data_val, param_.data_format,
-                                         static_cast<unsigned>(part), static_cast<unsigned>(nparts),
-                                         train ? static_cast<unsigned>(param_.batch_size) : 65536u,
-                                         train ? static_cast<unsigned>(param_.batch_size) * static_cast<unsigned>(param_.shuffle) : 0u,
-                                         train ? param_.neg_sampling : 1.0f, static_cast<unsigned>(epoch)));
-          }
-          if (reader->Next()) return true;
-          reader.reset();
-          part += N;
-        }
-      };
       for (;;) {
-        bool has = false;
-        if (errors[r].empty()) {
-          try { has = next(); } catch (const std::exception& e) { errors[r] = e.what(); }
+        if (!me.reader) {
+          if (me.part >= nparts) return;
+          me.reader.reset(new BatchReader(train ? param_.data_in : param_.data_val, param_.data_format,
+                                          static_cast<unsigned>(me.part), static_cast<unsigned>(nparts),
+                                          train ? static_cast<unsigned>(param_.batch_size) : 65536u,
+                                          train ? static_cast<unsigned>(param_.batch_size) * static_cast<unsigned>(param_.shuffle) : 0u,
+                                          train ? param_.neg_sampling : 1.0f, static_cast<unsigned>(epoch)));
         }
-        if (!barrier.Sync(has)) break;
-        dfb_progress pr;
-        if (has) {
-          const auto blk = reader->Value();
-          eng->Check(dfb_shard_step_async(eng->handle(), blk.size, reinterpret_cast<const uint64_t*>(blk.offset), blk.index,
-                                          blk.value, blk.label, push_cnt ? 1 : 0, train ? 1 : 0), "dfb_shard_step_async");
-        } else {
-          eng->Check(dfb_shard_step_async(eng->handle(), 0, nullptr, nullptr, nullptr, nullptr, push_cnt ? 1 : 0, train ? 1 : 0),
-                     "dfb_shard_step_async");
-        }
-        eng->Check(dfb_wait_step(eng->handle(), &pr), "dfb_wait_step");
-        progs[r].loss += pr.loss; progs[r].penalty += pr.penalty; progs[r].auc += pr.auc; progs[r].nrows += pr.nrows;
+        if (me.reader->Next()) { me.has = true; return; }
+        me.reader.reset();
+        me.part += N;
       }
     } catch (const std::exception& e) {
-      errors[r] = e.what();
-      // leave the collective cleanly: the other workers would wait for this one's step counters only until
-      // shard_timeout_ms, then report DFB_ERR_TIMEOUT themselves
+      me.error = e.what();
     }
   };
-  std::vector<std::thread> th;
-  for (int r = 0; r < N; ++r) th.emplace_back(worker, r);
-  for (auto& t : th) t.join();
-  for (int r = 0; r < N; ++r) if (!errors[r].empty()) throw Error("worker " + std::to_string(r) + ": " + errors[r]);
-  for (int r = 0; r < N; ++r) prog->Merge(progs[r]);
+  for (;;) {
+    {
+      std::vector<std::thread> th;
+      for (int r = 0; r < N; ++r) th.emplace_back(next, r);
+      for (auto& t : th) t.join();
+    }
+    bool any = false;
+    for (int r = 0; r < N; ++r) {
+      if (!w[r].error.empty()) throw Error("worker " + std::to_string(r) + ": " + w[r].error);
+      any = any || w[r].has;
+    }
+    if (!any) break;
+    for (int r = 0; r < N; ++r) {
+      const auto& eng = ShardEngine(r);
+      if (w[r].has) {
+        const auto blk = w[r].reader->Value();
+        eng->Check(dfb_shard_begin_async(eng->handle(), blk.size, reinterpret_cast<const uint64_t*>(blk.offset), blk.index,
+                                         blk.value, blk.label, push_cnt ? 1 : 0, train ? 1 : 0), "dfb_shard_begin_async");
+      } else {
+        eng->Check(dfb_shard_begin_async(eng->handle(), 0, nullptr, nullptr, nullptr, nullptr, push_cnt ? 1 : 0, train ? 1 : 0),
+                   "dfb_shard_begin_async");
+      }
+    }
+    for (int ph = 0; ph < 5; ++ph)
+      for (int r = 0; r < N; ++r) ShardEngine(r)->Check(dfb_shard_phase(ShardEngine(r)->handle(), ph), "dfb_shard_phase");
+    for (int r = 0; r < N; ++r) {
+      dfb_progress pr;
+      ShardEngine(r)->Check(dfb_wait_step(ShardEngine(r)->handle(), &pr), "dfb_wait_step");
+      prog->loss += pr.loss; prog->penalty += pr.penalty; prog->auc += pr.auc; prog->nrows += pr.nrows;
+    }
+  }
 }
 
 // SGDLearner::GetPos, sgd_learner.cc:113-127
