@@ -334,10 +334,14 @@ int dfb_shard_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, con
                          const float* value_or_null, const float* label, int push_cnt, int is_train);
 /* The same step split into its five enqueue phases (0 worker: localize + scatter the slices, 1 owner: lookup +
  * partial sums, 2 worker: reduce + p*XV back, 3 owner: updates, 4 finish): dfb_shard_step_* is begin + phases
- * 0..4.  Needed only when ONE host thread drives several engines that share ONE device (tests): there the
- * phases must be interleaved -- phase p of every engine before phase p+1 of any -- so that every device-side
- * wait refers to work that is already enqueued.  Engines on different devices (or driven by different
- * threads / processes) just call dfb_shard_step_*. */
+ * 0..4.  Needed whenever ONE host thread drives several ranks (the C++ CLI's num_gpus = N, the one-device tests):
+ * the phases must be interleaved -- phase p of every rank before phase p+1 of any -- so that every device-side
+ * wait refers to work that is already enqueued.  With monolithic steps, rank 0's pollers would wait for work
+ * the thread has not enqueued yet; on one device that never completes, and on several devices it deadlocks as
+ * soon as a driver call in between blocks (a lazily loaded kernel synchronises its context).  Ranks that have a
+ * host thread or a process of their own just call dfb_shard_step_*.
+ * On the wire every minibatch is valued (x = 1 for a binary one), so the workers of a step may hold any mix of
+ * binary, valued and empty minibatches. */
 int dfb_shard_begin_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
                           const float* value_or_null, const float* label, int push_cnt, int is_train);
 int dfb_shard_phase(dfb_handle h, int phase);

@@ -272,6 +272,6 @@ def test_cli_two_gpus_sharded_store(host_bin, tmp_path):
     assert os.path.exists(model + "_part-0") and os.path.exists(model + "_part-1")
     # the saved shards, reloaded and scored by two GPUs again (task=predict): the validation loss they were saved with
     again = subprocess.run([exe, "task=predict", f"data_in={val}", f"model_in={model}", "num_gpus=2", "V_dim=16",
-                            "table_capacity=65536"], capture_output=True, text=True, timeout=300)
+                            "batch_size=200", "table_capacity=65536"], capture_output=True, text=True, timeout=300)
     assert again.returncode == 0, again.stderr[-2000:]
     assert losses(again, "Prediction")[0] == pytest.approx(v2[-1], rel=1e-4)
