@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--nnz", type=int, default=100)
     ap.add_argument("--vdim", type=int, default=64)
     ap.add_argument("--id-space", type=int, default=10 ** 9)
-    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "criteo39"])
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "criteo39", "gisette"])
     ap.add_argument("--hyper", default="allV", choices=["allV", "criteo_conf", "ftrl_l1"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the short runs of the other named configs")
     ap.add_argument("--cold", action="store_true", help="cold table: every timed batch brings only new keys")
@@ -71,10 +71,24 @@ def reverse_bytes_np(x):
     return x
 
 
+GISETTE_NNZ = 5000      # gisette: 5000 dense features per example (the "long row" shape)
+
+
+def nnz_of(args):
+    return {"synthetic": args.nnz, "criteo39": 39, "gisette": GISETTE_NNZ}[args.workload]
+
+
 def gen_raw_batch(args, seed, rows=None):
-    """raw (un-localized) CSR<u64> minibatch of the named shape"""
+    """raw (un-localized) CSR<u64> minibatch of the named shape: (offset, label, ids[, values])"""
     rng = np.random.default_rng(seed)
     B = rows or args.batch
+    if args.workload == "gisette":
+        # every example holds all 5000 features, real-valued (gisette's pixel features scaled to [0, 1))
+        nnz = GISETTE_NNZ
+        ids = np.tile(np.arange(1, nnz + 1, dtype=np.uint64), B)
+        off = (np.arange(B + 1, dtype=np.uint64) * np.uint64(nnz))
+        lab = np.where(rng.random(B) < 0.5, 1.0, -1.0).astype(np.float32)
+        return off, lab, ids, (rng.random(B * nnz, dtype=np.float32) * np.float32(0.02))
     if args.workload == "criteo39":
         # 13 "integer" + 26 "categorical" groups, id = (hash << 12) | group (criteo_parser.h:68-88), Zipf-ish hashes
         nnz = 39
@@ -86,7 +100,7 @@ def gen_raw_batch(args, seed, rows=None):
         ids = rng.integers(0, args.id_space, B * nnz).astype(np.uint64)
     off = (np.arange(B + 1, dtype=np.uint64) * np.uint64(nnz))
     lab = np.where(rng.random(B) < 0.25, 1.0, -1.0).astype(np.float32)
-    return off, lab, ids
+    return off, lab, ids, None
 
 
 def localize_np(ids):
@@ -183,22 +197,22 @@ def cpu_reference_run(args, steps, warmup, nthreads=None, rows=None):
     eng = O.RefOracle(nthreads=nthreads, **kw) if kind == "reference" else O.Oracle(**kw)
     # table warm-up: two passes so that every key of the sample has reached its steady state (as on the GPU arm)
     for p in range(2):
-        for (off, lab, ids) in batches:
-            eng.sgd_step(off, ids, None, lab, True, p == 0)
+        for (off, lab, ids, val) in batches:
+            eng.sgd_step(off, ids, val, lab, True, p == 0)
     for t in range(warmup):
-        off, lab, ids = batches[t % nb]
-        eng.sgd_step(off, ids, None, lab, True, False)
+        off, lab, ids, val = batches[t % nb]
+        eng.sgd_step(off, ids, val, lab, True, False)
     secs = np.zeros(6, np.float64)
     t0 = time.perf_counter()
     for t in range(steps):
-        off, lab, ids = batches[t % nb]
+        off, lab, ids, val = batches[t % nb]
         if kind == "reference":
-            eng.sgd_step(off, ids, None, lab, True, False, seconds=secs)
+            eng.sgd_step(off, ids, val, lab, True, False, seconds=secs)
         else:
-            eng.sgd_step(off, ids, None, lab, True, False)
+            eng.sgd_step(off, ids, val, lab, True, False)
     dt = time.perf_counter() - t0
     ex_s = steps * rows / dt
-    sample = (f"{steps} steps x {rows} rows x {args.nnz if args.workload == 'synthetic' else 39} nnz "
+    sample = (f"{steps} steps x {rows} rows x {nnz_of(args)} nnz "
               f"(same shape/hyper-parameters, table warmed, Localizer::Compact included)")
     return dict(value=ex_s, unit="examples/s", cores=int(nthreads if kind == "reference" else 1), kind=kind,
                 sample=sample, ms_per_step=dt / steps * 1e3, host_cores=cores, rows=rows,
@@ -231,11 +245,13 @@ def metric_name(args):
 
 
 def workload_config(args, extra):
-    nnz = args.nnz if args.workload == "synthetic" else 39
+    nnz = nnz_of(args)
     cfg = {"workload": (f"synthetic CSR (BASELINE.json configs[4] / SURVEY 8d 'S'): batch {args.batch} x {nnz} nnz/row, "
                         f"ids uniform over [0,{args.id_space}), binary values, V_dim={args.vdim}"
                         + (", every key owns a V row" if args.hyper == "allV" else f", hyper={args.hyper}")
                         if args.workload == "synthetic" else
+                        f"gisette-shaped CSR: batch {args.batch} x {GISETTE_NNZ} dense real-valued features, V_dim={args.vdim}, "
+                        f"hyper={args.hyper}" if args.workload == "gisette" else
                         f"criteo-shaped CSR: batch {args.batch} x 39 nnz/row, Zipf ids with 12-bit group id, "
                         f"V_dim={args.vdim}, hyper={args.hyper}"),
            "global_batch": args.batch * args.gpus, "batch_per_gpu": args.batch, "nnz_per_row": nnz, "V_dim": args.vdim,
@@ -277,9 +293,10 @@ def byte_model(B, N, U, k):
 def gen_raw_set(args, nb, seed0, torch, rows=None):
     out = []
     for b in range(nb):
-        off, lab, ids = gen_raw_batch(args, seed0 + b, rows=rows)
+        off, lab, ids, val = gen_raw_batch(args, seed0 + b, rows=rows)
         out.append(dict(off=torch.from_numpy(off.view(np.int64)).pin_memory(), lab=torch.from_numpy(lab).pin_memory(),
-                        ids=torch.from_numpy(ids.view(np.int64)).pin_memory(), nnz=len(ids), nrows=len(lab)))
+                        ids=torch.from_numpy(ids.view(np.int64)).pin_memory(), nnz=len(ids), nrows=len(lab),
+                        val=torch.from_numpy(val).pin_memory() if val is not None else None))
     return out
 
 
@@ -290,7 +307,7 @@ def run_single(args, local_rank, full, sampler=None):
     from difacto_b200 import capi
     dev = torch.device("cuda", local_rank)
     kw = hyper(args)
-    nnz_row = args.nnz if args.workload == "synthetic" else 39
+    nnz_row = nnz_of(args)
     B, k = args.batch, args.vdim
     N = B * nnz_row
     steps, warm = args.steps, args.warmup
@@ -321,15 +338,16 @@ def run_single(args, local_rank, full, sampler=None):
         localizer_check = bool(np.array_equal(gl, nl) and np.array_equal(gk, nk) and np.array_equal(gc, nc))
     probe.close()
     cap = int(nb * U0 * 1.05) + 4096
-    id_bits = int(np.ceil(np.log2(float(max(args.id_space * (nb if cold else 1), 2))))) if args.workload == "synthetic" else 64
+    id_bits = int(np.ceil(np.log2(float(max(args.id_space * (nb if cold else 1), 2))))) if args.workload == "synthetic" else (13 if args.workload == "gisette" else 64)
     E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap, id_bits=min(id_bits, 64),
                     overlap_auc=0 if args.no_overlap_auc else 1, **extra, **kw)
-    devb = [dict(off=h["off"].to(dev), lab=h["lab"].to(dev), ids=h["ids"].to(dev)) for h in host]
+    devb = [dict(off=h["off"].to(dev), lab=h["lab"].to(dev), ids=h["ids"].to(dev),
+                 val=h["val"].to(dev) if h["val"] is not None else None) for h in host]
     torch.cuda.synchronize()
 
     def step_dev(b, push_cnt=False, train=True):
         d = devb[b]
-        E.train_step_raw_dev(B, N, d["off"], d["ids"], None, d["lab"], push_cnt, train)
+        E.train_step_raw_dev(B, N, d["off"], d["ids"], d["val"], d["lab"], push_cnt, train)
 
     if not cold:
         # table warm-up (untimed): two passes, after which every key has reached its steady state
@@ -393,10 +411,10 @@ def run_single(args, local_rank, full, sampler=None):
     if full and not args.no_e2e:
         def submit_raw(b, nxt=None):
             r = host[b]
-            E.train_step_raw_async(B, r["off"], r["ids"], None, r["lab"], False, True)
+            E.train_step_raw_async(B, r["off"], r["ids"], r["val"], r["lab"], False, True)
             if nxt is not None:       # start the H2D of the next batch while this step runs
                 n_ = host[nxt]
-                E.prefetch_raw(B, n_["off"], n_["ids"], None, n_["lab"])
+                E.prefetch_raw(B, n_["off"], n_["ids"], n_["val"], n_["lab"])
         for t in range(warm):
             submit_raw(t % nb)
         E.read_progress()
@@ -412,7 +430,7 @@ def run_single(args, local_rank, full, sampler=None):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         out["e2e"] = {"value": steps * B / dt, "unit": "examples/s",
-                      "h2d_bytes_per_step": int((B + 1) * 8 + N * 8 + B * 4), "d2h_bytes_per_step": 64,
+                      "h2d_bytes_per_step": int((B + 1) * 8 + N * 8 + B * 4 + (N * 4 if host[0]["val"] is not None else 0)), "d2h_bytes_per_step": 64,
                       "ms_per_step": dt / steps * 1e3, "mean_loss_per_step": loss_sum / steps,
                       "api": "dfb_train_step_raw_async (+ dfb_prefetch_raw) + dfb_wait_step: raw uint64 CSR from pinned "
                              "host memory, Localizer::Compact on the GPU, then the fused step; nothing else is "
@@ -425,7 +443,7 @@ def run_single(args, local_rank, full, sampler=None):
 
 
 def roofline_of(args, res, peak):
-    nnz_row = args.nnz if args.workload == "synthetic" else 39
+    nnz_row = nnz_of(args)
     B, k = args.batch, args.vdim
     N, U = B * nnz_row, res["unique_keys_per_batch"]
     fwd, emit, upd, step = byte_model(B, N, U, k)
@@ -453,7 +471,11 @@ def sweep_configs(args):
             ("criteo39_V64_conf", cfg(workload="criteo39", vdim=64, hyper="criteo_conf")),
             ("criteo39_V64_allV", cfg(workload="criteo39", vdim=64, hyper="allV")),
             ("criteo39_V32_ftrl_l1", cfg(workload="criteo39", vdim=32, hyper="ftrl_l1")),
-            ("synthetic_V64_cold_table", cfg(vdim=64, cold=True))]
+            ("synthetic_V64_cold_table", cfg(vdim=64, cold=True)),
+            # long rows: 1024 examples x 5000 dense features (5.1 M nnz per step); CTA-per-row forward vs warp-per-row
+            ("gisette_V64_long_rows", cfg(workload="gisette", batch=1024, vdim=64)),
+            ("gisette_V64_warp_per_row", cfg(workload="gisette", batch=1024, vdim=64,
+                                             engine_kw=",".join(x for x in (args.engine_kw, "long_row_nnz=0") if x)))]
 
 
 def main_b200(args, rank, world, local_rank):
@@ -469,7 +491,7 @@ def main_b200(args, rank, world, local_rank):
     time.sleep(0.3)
     res = run_single(args, local_rank, full=True)
     clocks = sampler.summary(res["wall"][0], res["wall"][1])
-    nnz_row = args.nnz if args.workload == "synthetic" else 39
+    nnz_row = nnz_of(args)
     B, k = args.batch, args.vdim
     rf = roofline_of(args, res, peak)
     traffic = None

@@ -165,6 +165,10 @@ struct FmBatch {
   float* pxv_out;           //   p_i * XV_i                             [nrows][V_dim]
   uint32_t* occ_row;        //   row of every nnz (binary data)         [nnz]
   unsigned long long* occ_rowx;  // (row << 32 | bits(x)) (valued data) [nnz]
+  // long rows (predict / emit on the fast path): rows of >= long_nnz nonzeros are left to k_fm_long, where a whole
+  // CTA walks one row (0 = one warp per row whatever its length); nnz_hint = the batch's nnz when the host knows it
+  unsigned long_nnz;
+  size_t nnz_hint;
 };
 
 // true when launch_fm would take the 16-byte-lane fast path for this V_dim / view

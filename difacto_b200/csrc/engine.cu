@@ -271,6 +271,7 @@ int step_dev(dfb_engine* h, size_t nrows, size_t nnz, const uint64_t* d_off, con
   b.nrows = nrows; b.offset = d_off; b.index = d_idx; b.value = d_val; b.label = d_lab;
   b.pred_in = nullptr; b.pred_io = h->pred.as<float>(); b.pred_acc = 0;
   b.V_dim = h->prm.V_dim; b.train = is_train; b.prog = h->tab.prog;
+  b.long_nnz = (unsigned)h->long_row_nnz; b.nnz_hint = nnz;
   if (sorted) {
     b.emit = 1; b.p_out = h->p_row.as<float>(); b.pxv_out = h->pxv.as<float>();
     b.occ_row = csc_ready ? nullptr : h->occ.as<uint32_t>();
@@ -567,6 +568,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     else if (k == "lookup_ilp") { if (!need_int(1, 4)) { delete h; return DFB_ERR_PARAM; } g_lookup_ilp = (int)x; }
     else if (k == "lookup_ctas") { if (!need_int(1, 64)) { delete h; return DFB_ERR_PARAM; } g_lookup_ctas = (int)x; }
     else if (k == "k1_tma") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->k1_tma = (int)x; }
+    else if (k == "long_row_nnz") { if (!need_int(0, 1 << 30)) { delete h; return DFB_ERR_PARAM; } h->long_row_nnz = (int)x; }
     else if (k == "hot_split") { if (!need_int(0, 1 << 30)) { delete h; return DFB_ERR_PARAM; } h->hot_split = (int)x; }
     else if (k == "l2_hints") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->l2_hints = (int)x; }
     else if (k == "id_bits") { if (!need_int(0, 64)) { delete h; return DFB_ERR_PARAM; } h->id_bits = (int)x; }
@@ -1546,6 +1548,7 @@ static int dev_fm_step_impl(dfb_handle h, size_t nrows, size_t nnz, const uint64
   memset(&b, 0, sizeof(b));
   b.nrows = nrows; b.offset = d_offset; b.index = d_index; b.value = d_value; b.label = d_label;
   b.pred_io = h->pred.as<float>(); b.V_dim = k; b.train = is_train; b.prog = h->tab.prog;
+  b.long_nnz = (unsigned)h->long_row_nnz; b.nnz_hint = nnz;
   if (sorted) {
     b.emit = 1; b.p_out = h->p_row.as<float>(); b.pxv_out = h->pxv.as<float>();
     b.occ_row = h->occ.as<uint32_t>(); b.occ_rowx = h->occ.as<unsigned long long>();

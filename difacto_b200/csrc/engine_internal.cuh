@@ -31,6 +31,7 @@ struct dfb_engine {
   int loc_begin_bit = -1;   // auto mode: lowest significant bit of the reversed keys seen so far (sticky)
   long long shard_timeout_ms = 20000;
   int k1_tma = 0;           // 1: validation batches use the bulk-copy staged gather kernel (kernels_fm_tma.cu)
+  int long_row_nnz = 1024;  // rows with at least this many nonzeros are walked by a whole CTA (k_fm_long); 0: off
   int hot_split = 256;      // occurrence lists longer than this are pre-reduced in chunks by separate warps (0: off)
   cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;
   cudaEvent_t ev_fm_done = nullptr, ev_auc_done = nullptr;

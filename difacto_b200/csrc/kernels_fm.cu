@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
       offp = pa.s[src].rowptr; idxp = pa.s[src].ridx; valp = pa.s[src].rval; wvp = pa.s[src].wv;
     }
     const uint64_t o0 = offp[row], o1 = offp[row + 1];
+    if ((MODE == 0 || MODE == 2) && b.long_nnz && o1 - o0 >= b.long_nnz) continue;   // k_fm_long's row
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     float acc2 = 0.f, wsum = 0.f;
 
@@ -273,6 +274,122 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
     }
   }
   if (MODE != 3) block_add_loss(loss_acc, b.nrows, b.prog);
+}
+
+// ---------------------------------------------------------------------------------------
+// long rows (gisette: ~5000 nonzeros per example): one CTA per row.  A single warp would walk such a row as
+// ~nnz/16 dependent gather rounds with 32 lanes of loads in flight; here the 8 warps of a CTA take the row's
+// 32-nnz chunks round-robin, and their partial (XV, sum (xV)^2, sum xw) are added in warp order through shared
+// memory (fixed order: bit-reproducible).  Rows shorter than b.long_nnz are k_fm_fast's.  MODE 0 / 2 as above.
+// ---------------------------------------------------------------------------------------
+constexpr int kLongWarps = 8;
+
+template <int K, int MODE, bool HAS_VAL>
+__global__ void __launch_bounds__(kLongWarps * 32) k_fm_long(FmBatch b, FmView v) {
+  constexpr int LPR = K / 4;
+  constexpr int G = 32 / LPR;
+  constexpr int UNR = (32 / G) < 8 ? (32 / G) : 8;
+  __shared__ float4 s_xv[kLongWarps][LPR];
+  __shared__ float2 s_sc[kLongWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const uint64_t pol_v = l2_policy(v.l2hint ? 1 : 0), pol_wv = l2_policy(v.l2hint ? 2 : 0);
+  float loss_acc = 0.f;                       // thread 0 only
+
+  for (size_t row = blockIdx.x; row < b.nrows; row += gridDim.x) {
+    const uint64_t o0 = b.offset[row], o1 = b.offset[row + 1];
+    if (o1 - o0 < b.long_nnz) continue;       // CTA-uniform
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc2 = 0.f, wsum = 0.f;
+    for (uint64_t c = o0 + 32u * wid; c < o1; c += 32u * kLongWarps) {
+      const uint64_t j = c + lane;
+      float x = 0.f, w = 0.f;
+      int vr = -1;
+      if (j < o1) {
+        const uint32_t u = __ldg(b.index + j);
+        x = HAS_VAL ? __ldg(b.value + j) : 1.f;
+        if (v.wv) {
+          const int2 t = ldg64_pol(v.wv + u, pol_wv);
+          w = __int_as_float(t.x);
+          vr = t.y;
+        } else {
+          const int wp = v.w_pos ? __ldg(v.w_pos + u) : (int)u;
+          w = wp >= 0 ? __ldg(v.wbase + wp) : 0.f;
+          vr = __ldg(v.v_pos + u);
+          if (v.dense && vr >= 0) vr = (int)u;
+        }
+        if (MODE == 2 && b.occ_row != nullptr) {
+          if (HAS_VAL) b.occ_rowx[j] = ((unsigned long long)row << 32) | (unsigned long long)__float_as_uint(x);
+          else b.occ_row[j] = (uint32_t)row;
+        }
+      }
+      wsum = fmaf(x, w, wsum);
+      const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
+      for (int t0 = 0; t0 < cnt; t0 += G * UNR) {
+        float4 vv[UNR];
+        float xs[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const int t = t0 + q * G + grp;
+          const int vr_t = __shfl_sync(kFull, vr, t & 31);
+          const float x_t = __shfl_sync(kFull, x, t & 31);
+          const bool ok = (t < cnt) && (vr_t >= 0);
+          xs[q] = ok ? x_t : 0.f;
+          vv[q] = ok ? ldg128_pol(v.vbase + (long long)vr_t * v.vstride + sub * 4, pol_v)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const float a0 = xs[q] * vv[q].x, a1 = xs[q] * vv[q].y;
+          const float a2 = xs[q] * vv[q].z, a3 = xs[q] * vv[q].w;
+          xv.x += a0; xv.y += a1; xv.z += a2; xv.w += a3;
+          acc2 = fmaf(a0, a0, acc2); acc2 = fmaf(a1, a1, acc2);
+          acc2 = fmaf(a2, a2, acc2); acc2 = fmaf(a3, a3, acc2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      xv.x += __shfl_xor_sync(kFull, xv.x, o);
+      xv.y += __shfl_xor_sync(kFull, xv.y, o);
+      xv.z += __shfl_xor_sync(kFull, xv.z, o);
+      xv.w += __shfl_xor_sync(kFull, xv.w, o);
+    }
+    acc2 = warp_sum(acc2);
+    wsum = warp_sum(wsum);
+    if (grp == 0) s_xv[wid][sub] = xv;
+    if (lane == 0) s_sc[wid] = make_float2(acc2, wsum);
+    __syncthreads();
+    if (wid == 0) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      float a2 = 0.f, ws = 0.f;
+#pragma unroll
+      for (int q = 0; q < kLongWarps; ++q) {
+        const float4 e = s_xv[q][sub];
+        t.x += e.x; t.y += e.y; t.z += e.z; t.w += e.w;
+        a2 += s_sc[q].x; ws += s_sc[q].y;
+      }
+      float s1 = grp == 0 ? (t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w) : 0.f;
+      s1 = warp_sum(s1);
+      float pred = (b.pred_acc ? b.pred_io[row] : 0.f) + ws;
+      pred += 0.5f * (s1 - a2);
+      pred = pred > 20.f ? 20.f : (pred < -20.f ? -20.f : pred);   // fm_loss.h:118
+      const float label = b.label ? __ldg(b.label + row) : 0.f;
+      if (lane == 0) {
+        if (b.pred_io) b.pred_io[row] = pred;
+        if (b.label) loss_acc += row_logloss(label, pred);
+      }
+      if (MODE == 2) {
+        const float p = row_p(label, pred);
+        if (lane == 0) b.p_out[row] = p;
+        if (grp == 0)
+          *reinterpret_cast<float4*>(b.pxv_out + row * (size_t)K + sub * 4) = make_float4(p * t.x, p * t.y, p * t.z, p * t.w);
+      }
+    }
+    __syncthreads();
+  }
+  // (nrows is counted by k_fm_fast)
+  if (threadIdx.x == 0 && b.prog && loss_acc != 0.f) atomicAdd(&b.prog->loss, (double)loss_acc);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -423,6 +540,18 @@ int launch_fast_k(const FmBatch& b, const FmView& v, cudaStream_t s) {
   } else {
     if (hv) k_fm_fast<K, 0, true><<<grid, threads, 0, s>>>(b, v, pa);
     else    k_fm_fast<K, 0, false><<<grid, threads, 0, s>>>(b, v, pa);
+  }
+  // rows of >= long_nnz nonzeros: one CTA each (the scan over the offsets costs ~1 us when there is none)
+  if (b.long_nnz && (!b.train || b.emit) && (b.nnz_hint == 0 || b.nnz_hint >= b.long_nnz)) {
+    const int lgrid = (int)(b.nrows < (size_t)(148 * 4) ? b.nrows : (size_t)(148 * 4));
+    if (b.train) {
+      if (hv) k_fm_long<K, 2, true><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
+      else    k_fm_long<K, 2, false><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
+    } else {
+      if (hv) k_fm_long<K, 0, true><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
+      else    k_fm_long<K, 0, false><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
+    }
+    return 2;
   }
   return 1;
 }

@@ -81,6 +81,10 @@ typedef struct {
  *                         verified on the device afterwards; a later batch with wider ids is dropped with
  *                         DFB_ERR_INVALID (pass id_bits, or use the synchronous dfb_train_step_raw)
  *   shard_timeout_ms (20000)  how long a rank of the sharded store waits for a peer
+ *   hot_split (256)       a key with more occurrences in a minibatch than this has its gradient pre-reduced in
+ *                         chunks by separate warps, then finished in chunk order (0: one warp per key)
+ *   long_row_nnz (1024)   an example with at least this many nonzeros is walked by a whole CTA in the forward
+ *                         kernel, its chunks added in a fixed order (0: one warp per example whatever its length)
  *   force_generic (0)     1 = use the any-V_dim kernels even where a specialised one exists (tests)
  * Keys that are neither are returned through dfb_unknown_kwarg, mirroring the
  * "return the unconsumed kwargs" convention (updater.h:34, main.cc:25-31).

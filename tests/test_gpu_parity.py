@@ -350,6 +350,35 @@ def test_edge_cases_empty_rows_and_batches():
     compare_state(M, E, localized((off, lab, idx, val))["keys"])
 
 
+@pytest.mark.parametrize("V_dim,valued", [(16, True), (64, False), (128, True)])
+def test_long_rows_cta_per_row_vs_oracle(V_dim, valued):
+    """gisette-shaped examples (5000 nonzeros) next to rows just below / at / above long_row_nnz, short and empty
+    ones: rows of >= long_row_nnz nonzeros are walked by a whole CTA (k_fm_long), the others by one warp
+    (k_fm_fast) -- trajectory and predictions against the oracle, and against the engine with the long path off"""
+    rng = np.random.default_rng(9)
+    lens = np.array([5000, 0, 1023, 1024, 1025, 40, 4999, 7, 2048, 0, 3], np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    n = int(off[-1])
+    idx = rng.integers(0, 5000, n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    val = (rng.random(n).astype(np.float32) * 0.05) if valued else None
+    lab = np.where(rng.random(len(lens)) < 0.5, 1.0, -1.0).astype(np.float32)
+    kw = dict(V_dim=V_dim, l1=0.01, l2=0.01, lr=0.05, V_lr=0.02, V_threshold=0, V_init_scale=0.01 if valued else 0.002,
+              seed=5)
+    M = O.Oracle(**kw)
+    E = engine(**kw)
+    W = engine(long_row_nnz=0, **kw)
+    for t in range(4):
+        is_train = t != 2
+        ref = M.sgd_step(off, idx, val, lab, is_train, t == 0)
+        pr, pred = E.train_step_raw(off, idx, val, lab, push_cnt=(t == 0), is_train=is_train, want_pred=True)
+        prw, predw = W.train_step_raw(off, idx, val, lab, push_cnt=(t == 0), is_train=is_train, want_pred=True)
+        assert abs(pr.loss - ref[0]) <= 1e-4 * abs(ref[0]) + 1e-5, f"step {t}: {pr.loss} vs {ref[0]}"
+        assert_close(pred, predw, what=f"CTA-per-row vs warp-per-row pred, step {t}", rtol=1e-4, atol=1e-5)
+    keys = localized((off, lab, idx, val))["keys"]
+    compare_state(M, E, keys)
+    compare_state(M, W, keys)
+
+
 def test_validation_step_does_not_update():
     rng = np.random.default_rng(11)
     kw = dict(V_dim=16, l1=0.01, lr=0.1, V_threshold=0, seed=4)
@@ -485,6 +514,38 @@ def test_full_size_properties(V_dim):
     # 3. checksum: sum_keys grad_w == sum_rows p_i * nnz_i  <=> after one more FTRL step with l1=l2=0
     #    the table still holds exactly len(keys) keys and AUC is in [0.5, 1] * B
     assert 0.5 * B <= prE.auc <= B
+
+
+def test_full_size_training_steps_vs_oracle():
+    """BASELINE.json's synthetic shape (65536 rows x 100 nnz, raw uint64 ids) through the fused raw-id step -- GPU
+    localizer, lookup/insert, InitV, forward, per-key gradient reduce, FTRL/AdaGrad -- against the oracle running the
+    SAME three minibatches (about 12 s of CPU per step): loss and penalty per step, and the full state of a 4000-key
+    sample (plus the 200 most frequent keys) after the third update.  V_dim = 16 keeps the oracle's share bearable."""
+    B, NNZ, k = 65536, 100, 16
+    rng = np.random.default_rng(78)
+    off = (np.arange(B + 1, dtype=np.uint64) * np.uint64(NNZ))
+    kw = dict(V_dim=k, l1=0.02, l2=0.01, lr=0.05, V_lr=0.05, V_l2=0.01, V_threshold=2, V_init_scale=0.05, seed=2)
+    M = O.Oracle(**kw)
+    E = capi.Engine(table_capacity=1 << 25, **kw)
+    seen = []
+    for t in range(3):
+        # a skewed head (hot keys, V rows appear after two counts) over a uniform tail (mostly new keys every step)
+        hot = rng.zipf(1.3, B * NNZ) % 5000
+        ids = np.where(rng.random(B * NNZ) < 0.3, hot, rng.integers(0, 3 * 10 ** 7, B * NNZ)).astype(np.uint64)
+        ids *= np.uint64(0x9E3779B97F4A7C15)
+        lab = np.where(rng.random(B) < 0.3, 1.0, -1.0).astype(np.float32)
+        ref = M.sgd_step(off, ids, None, lab, True, True)
+        pr = E.train_step_raw(off, ids, None, lab, push_cnt=True, is_train=True)
+        assert pr.nrows == ref[4] == B
+        assert abs(pr.loss - ref[0]) <= 1e-4 * abs(ref[0]), f"loss step {t}: {pr.loss} vs {ref[0]}"
+        assert abs(pr.penalty - ref[1]) <= 1e-4 * abs(ref[1]) + 1e-5, f"penalty step {t}: {pr.penalty} vs {ref[1]}"
+        seen.append(ids)
+    assert E.table_stats()["n_keys"] == M.size()
+    assert E.rng_state() == M.seed()
+    allk, cnt = np.unique(O.reverse_bytes_np(np.concatenate(seen)), return_counts=True)
+    sample = np.unique(np.concatenate([rng.choice(allk, 4000, replace=False), allk[np.argsort(cnt)[-200:]]]))
+    hasv = compare_state(M, E, sample)
+    assert (hasv > 0).sum() > 200 and (hasv <= 0).sum() > 200      # both kinds of keys were compared
 
 
 def test_k1_bulk_copy_variant_equals_register_staged_kernel():
