@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, Fm
 constexpr int kLongWarps = 8;
 
 template <int K, int MODE, bool HAS_VAL>
-__global__ void __launch_bounds__(kLongWarps * 32) k_fm_long(FmBatch b, FmView v) {
+__global__ void __launch_bounds__(kLongWarps * 32) k_fm_long(FmBatch b, FmView v, int scan_rows) {
   constexpr int LPR = K / 4;
   constexpr int G = 32 / LPR;
   constexpr int UNR = (32 / G) < 8 ? (32 / G) : 8;
@@ -296,97 +296,110 @@ __global__ void __launch_bounds__(kLongWarps * 32) k_fm_long(FmBatch b, FmView v
   const uint64_t pol_v = l2_policy(v.l2hint ? 1 : 0), pol_wv = l2_policy(v.l2hint ? 2 : 0);
   float loss_acc = 0.f;                       // thread 0 only
 
-  for (size_t row = blockIdx.x; row < b.nrows; row += gridDim.x) {
-    const uint64_t o0 = b.offset[row], o1 = b.offset[row + 1];
-    if (o1 - o0 < b.long_nnz) continue;       // CTA-uniform
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    float acc2 = 0.f, wsum = 0.f;
-    for (uint64_t c = o0 + 32u * wid; c < o1; c += 32u * kLongWarps) {
-      const uint64_t j = c + lane;
-      float x = 0.f, w = 0.f;
-      int vr = -1;
-      if (j < o1) {
-        const uint32_t u = __ldg(b.index + j);
-        x = HAS_VAL ? __ldg(b.value + j) : 1.f;
-        if (v.wv) {
-          const int2 t = ldg64_pol(v.wv + u, pol_wv);
-          w = __int_as_float(t.x);
-          vr = t.y;
-        } else {
-          const int wp = v.w_pos ? __ldg(v.w_pos + u) : (int)u;
-          w = wp >= 0 ? __ldg(v.wbase + wp) : 0.f;
-          vr = __ldg(v.v_pos + u);
-          if (v.dense && vr >= 0) vr = (int)u;
+  // a CTA looks at scan_rows (<= 256, one per thread) row lengths at a time: with many rows per CTA the scan is one
+  // coalesced load (and almost always finds nothing); with few rows (a batch of long rows only) scan_rows is 1 and
+  // every CTA gets its own row
+  __shared__ unsigned char s_long[kLongWarps * 32];
+  for (size_t base = (size_t)blockIdx.x * scan_rows; base < b.nrows; base += (size_t)gridDim.x * scan_rows) {
+    const size_t mine = base + threadIdx.x;
+    bool is_long = false;
+    if ((int)threadIdx.x < scan_rows && mine < b.nrows) is_long = b.offset[mine + 1] - b.offset[mine] >= b.long_nnz;
+    s_long[threadIdx.x] = is_long ? 1 : 0;
+    if (!__syncthreads_or(is_long)) continue;
+    for (int r = 0; r < scan_rows; ++r) {                // in row order (the loss sum stays reproducible)
+      if (!s_long[r]) continue;                          // CTA-uniform
+      const size_t row = base + r;
+      const uint64_t o0 = b.offset[row], o1 = b.offset[row + 1];
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      float acc2 = 0.f, wsum = 0.f;
+      for (uint64_t c = o0 + 32u * wid; c < o1; c += 32u * kLongWarps) {
+        const uint64_t j = c + lane;
+        float x = 0.f, w = 0.f;
+        int vr = -1;
+        if (j < o1) {
+          const uint32_t u = __ldg(b.index + j);
+          x = HAS_VAL ? __ldg(b.value + j) : 1.f;
+          if (v.wv) {
+            const int2 t = ldg64_pol(v.wv + u, pol_wv);
+            w = __int_as_float(t.x);
+            vr = t.y;
+          } else {
+            const int wp = v.w_pos ? __ldg(v.w_pos + u) : (int)u;
+            w = wp >= 0 ? __ldg(v.wbase + wp) : 0.f;
+            vr = __ldg(v.v_pos + u);
+            if (v.dense && vr >= 0) vr = (int)u;
+          }
+          if (MODE == 2 && b.occ_row != nullptr) {
+            if (HAS_VAL) b.occ_rowx[j] = ((unsigned long long)row << 32) | (unsigned long long)__float_as_uint(x);
+            else b.occ_row[j] = (uint32_t)row;
+          }
         }
-        if (MODE == 2 && b.occ_row != nullptr) {
-          if (HAS_VAL) b.occ_rowx[j] = ((unsigned long long)row << 32) | (unsigned long long)__float_as_uint(x);
-          else b.occ_row[j] = (uint32_t)row;
+        wsum = fmaf(x, w, wsum);
+        const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
+        for (int t0 = 0; t0 < cnt; t0 += G * UNR) {
+          float4 vv[UNR];
+          float xs[UNR];
+  #pragma unroll
+          for (int q = 0; q < UNR; ++q) {
+            const int t = t0 + q * G + grp;
+            const int vr_t = __shfl_sync(kFull, vr, t & 31);
+            const float x_t = __shfl_sync(kFull, x, t & 31);
+            const bool ok = (t < cnt) && (vr_t >= 0);
+            xs[q] = ok ? x_t : 0.f;
+            vv[q] = ok ? ldg128_pol(v.vbase + (long long)vr_t * v.vstride + sub * 4, pol_v)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+  #pragma unroll
+          for (int q = 0; q < UNR; ++q) {
+            const float a0 = xs[q] * vv[q].x, a1 = xs[q] * vv[q].y;
+            const float a2 = xs[q] * vv[q].z, a3 = xs[q] * vv[q].w;
+            xv.x += a0; xv.y += a1; xv.z += a2; xv.w += a3;
+            acc2 = fmaf(a0, a0, acc2); acc2 = fmaf(a1, a1, acc2);
+            acc2 = fmaf(a2, a2, acc2); acc2 = fmaf(a3, a3, acc2);
+          }
         }
       }
-      wsum = fmaf(x, w, wsum);
-      const int cnt = (int)((o1 - c) < 32 ? (o1 - c) : 32);
-      for (int t0 = 0; t0 < cnt; t0 += G * UNR) {
-        float4 vv[UNR];
-        float xs[UNR];
-#pragma unroll
-        for (int q = 0; q < UNR; ++q) {
-          const int t = t0 + q * G + grp;
-          const int vr_t = __shfl_sync(kFull, vr, t & 31);
-          const float x_t = __shfl_sync(kFull, x, t & 31);
-          const bool ok = (t < cnt) && (vr_t >= 0);
-          xs[q] = ok ? x_t : 0.f;
-          vv[q] = ok ? ldg128_pol(v.vbase + (long long)vr_t * v.vstride + sub * 4, pol_v)
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+  #pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        xv.x += __shfl_xor_sync(kFull, xv.x, o);
+        xv.y += __shfl_xor_sync(kFull, xv.y, o);
+        xv.z += __shfl_xor_sync(kFull, xv.z, o);
+        xv.w += __shfl_xor_sync(kFull, xv.w, o);
+      }
+      acc2 = warp_sum(acc2);
+      wsum = warp_sum(wsum);
+      if (grp == 0) s_xv[wid][sub] = xv;
+      if (lane == 0) s_sc[wid] = make_float2(acc2, wsum);
+      __syncthreads();
+      if (wid == 0) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        float a2 = 0.f, ws = 0.f;
+  #pragma unroll
+        for (int q = 0; q < kLongWarps; ++q) {
+          const float4 e = s_xv[q][sub];
+          t.x += e.x; t.y += e.y; t.z += e.z; t.w += e.w;
+          a2 += s_sc[q].x; ws += s_sc[q].y;
         }
-#pragma unroll
-        for (int q = 0; q < UNR; ++q) {
-          const float a0 = xs[q] * vv[q].x, a1 = xs[q] * vv[q].y;
-          const float a2 = xs[q] * vv[q].z, a3 = xs[q] * vv[q].w;
-          xv.x += a0; xv.y += a1; xv.z += a2; xv.w += a3;
-          acc2 = fmaf(a0, a0, acc2); acc2 = fmaf(a1, a1, acc2);
-          acc2 = fmaf(a2, a2, acc2); acc2 = fmaf(a3, a3, acc2);
+        float s1 = grp == 0 ? (t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w) : 0.f;
+        s1 = warp_sum(s1);
+        float pred = (b.pred_acc ? b.pred_io[row] : 0.f) + ws;
+        pred += 0.5f * (s1 - a2);
+        pred = pred > 20.f ? 20.f : (pred < -20.f ? -20.f : pred);   // fm_loss.h:118
+        const float label = b.label ? __ldg(b.label + row) : 0.f;
+        if (lane == 0) {
+          if (b.pred_io) b.pred_io[row] = pred;
+          if (b.label) loss_acc += row_logloss(label, pred);
+        }
+        if (MODE == 2) {
+          const float p = row_p(label, pred);
+          if (lane == 0) b.p_out[row] = p;
+          if (grp == 0)
+            *reinterpret_cast<float4*>(b.pxv_out + row * (size_t)K + sub * 4) = make_float4(p * t.x, p * t.y, p * t.z, p * t.w);
         }
       }
+      __syncthreads();
     }
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-      xv.x += __shfl_xor_sync(kFull, xv.x, o);
-      xv.y += __shfl_xor_sync(kFull, xv.y, o);
-      xv.z += __shfl_xor_sync(kFull, xv.z, o);
-      xv.w += __shfl_xor_sync(kFull, xv.w, o);
-    }
-    acc2 = warp_sum(acc2);
-    wsum = warp_sum(wsum);
-    if (grp == 0) s_xv[wid][sub] = xv;
-    if (lane == 0) s_sc[wid] = make_float2(acc2, wsum);
-    __syncthreads();
-    if (wid == 0) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      float a2 = 0.f, ws = 0.f;
-#pragma unroll
-      for (int q = 0; q < kLongWarps; ++q) {
-        const float4 e = s_xv[q][sub];
-        t.x += e.x; t.y += e.y; t.z += e.z; t.w += e.w;
-        a2 += s_sc[q].x; ws += s_sc[q].y;
-      }
-      float s1 = grp == 0 ? (t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w) : 0.f;
-      s1 = warp_sum(s1);
-      float pred = (b.pred_acc ? b.pred_io[row] : 0.f) + ws;
-      pred += 0.5f * (s1 - a2);
-      pred = pred > 20.f ? 20.f : (pred < -20.f ? -20.f : pred);   // fm_loss.h:118
-      const float label = b.label ? __ldg(b.label + row) : 0.f;
-      if (lane == 0) {
-        if (b.pred_io) b.pred_io[row] = pred;
-        if (b.label) loss_acc += row_logloss(label, pred);
-      }
-      if (MODE == 2) {
-        const float p = row_p(label, pred);
-        if (lane == 0) b.p_out[row] = p;
-        if (grp == 0)
-          *reinterpret_cast<float4*>(b.pxv_out + row * (size_t)K + sub * 4) = make_float4(p * t.x, p * t.y, p * t.z, p * t.w);
-      }
-    }
-    __syncthreads();
+    __syncthreads();                                      // s_long is rewritten by the next scan
   }
   // (nrows is counted by k_fm_fast)
   if (threadIdx.x == 0 && b.prog && loss_acc != 0.f) atomicAdd(&b.prog->loss, (double)loss_acc);
@@ -544,12 +557,14 @@ int launch_fast_k(const FmBatch& b, const FmView& v, cudaStream_t s) {
   // rows of >= long_nnz nonzeros: one CTA each (the scan over the offsets costs ~1 us when there is none)
   if (b.long_nnz && (!b.train || b.emit) && (b.nnz_hint == 0 || b.nnz_hint >= b.long_nnz)) {
     const int lgrid = (int)(b.nrows < (size_t)(148 * 4) ? b.nrows : (size_t)(148 * 4));
+    int scan = 1;
+    while (scan < kLongWarps * 32 && (size_t)lgrid * scan * 2 <= b.nrows) scan *= 2;
     if (b.train) {
-      if (hv) k_fm_long<K, 2, true><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
-      else    k_fm_long<K, 2, false><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
+      if (hv) k_fm_long<K, 2, true><<<lgrid, kLongWarps * 32, 0, s>>>(b, v, scan);
+      else    k_fm_long<K, 2, false><<<lgrid, kLongWarps * 32, 0, s>>>(b, v, scan);
     } else {
-      if (hv) k_fm_long<K, 0, true><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
-      else    k_fm_long<K, 0, false><<<lgrid, kLongWarps * 32, 0, s>>>(b, v);
+      if (hv) k_fm_long<K, 0, true><<<lgrid, kLongWarps * 32, 0, s>>>(b, v, scan);
+      else    k_fm_long<K, 0, false><<<lgrid, kLongWarps * 32, 0, s>>>(b, v, scan);
     }
     return 2;
   }

@@ -17,65 +17,93 @@
 
 namespace difacto {
 
-/** one part of a text file: the lines that START inside byte range [size*i/n, size*(i+1)/n) */
+/**
+ * one part of a text file: the lines that START inside byte range [size*i/n, size*(i+1)/n), parsed as
+ * "label idx[:val] idx[:val] ..." (dmlc LibSVMParser semantics).  The part is streamed: the file is read in
+ * chunks of kChunkBytes and rows are handed out on demand, so the memory held is one chunk plus the caller's rows
+ * (the reference's Reader streams 64 MB chunks the same way, batch_reader.cc:26).
+ */
 class LibsvmPartReader {
  public:
-  LibsvmPartReader(const std::string& path, unsigned part, unsigned nparts) {
-    std::ifstream f(path, std::ios::binary | std::ios::ate);
-    if (!f) throw Error("failed to open " + path);
-    const size_t size = static_cast<size_t>(f.tellg());
+  static constexpr size_t kChunkBytes = 8u << 20;
+  LibsvmPartReader(const std::string& path, unsigned part, unsigned nparts, size_t chunk_bytes = kChunkBytes)
+      : f_(path, std::ios::binary | std::ios::ate), chunk_(chunk_bytes ? chunk_bytes : kChunkBytes) {
+    if (!f_) throw Error("failed to open " + path);
+    const size_t size = static_cast<size_t>(f_.tellg());
     size_t begin = size * part / nparts, end = size * (part + 1) / nparts;
     auto align = [&](size_t pos) {     // first line start at or after pos
       if (pos == 0 || pos >= size) return std::min(pos, size);
-      f.seekg(static_cast<std::streamoff>(pos - 1));
+      f_.seekg(static_cast<std::streamoff>(pos - 1));
       char c;
-      while (f.get(c)) { if (c == '\n') break; }
-      return f ? static_cast<size_t>(f.tellg()) : size;
+      while (f_.get(c)) { if (c == '\n') break; }
+      const size_t at = f_ ? static_cast<size_t>(f_.tellg()) : size;
+      f_.clear();
+      return at;
     };
-    begin = align(begin);
-    f.clear();
-    end = align(end);
-    f.clear();
-    buf_.resize(end > begin ? end - begin : 0);
-    f.seekg(static_cast<std::streamoff>(begin));
-    if (!buf_.empty()) f.read(&buf_[0], static_cast<std::streamsize>(buf_.size()));
+    next_ = align(begin);
+    end_ = align(end);
+    f_.seekg(static_cast<std::streamoff>(next_));
   }
-  /** parse everything: "label idx:val idx:val ..." per line (dmlc LibSVMParser semantics) */
-  void ParseAll(RowBlockContainer<feaid_t>* out) const {
-    out->Clear();
-    const char* p = buf_.data();
-    const char* e = p + buf_.size();
-    while (p < e) {
-      const char* le = static_cast<const char*>(memchr(p, '\n', static_cast<size_t>(e - p)));
-      if (!le) le = e;
-      const char* q = p;
-      while (q < le && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
-      if (q < le) {
-        char* nx = nullptr;
-        const float label = strtof(q, &nx);
-        if (nx != q) {
-          q = nx;
-          while (q < le) {
-            while (q < le && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
-            if (q >= le) break;
-            const feaid_t idx = strtoull(q, &nx, 10);
-            if (nx == q) break;
-            q = nx;
-            float val = 1.f;
-            if (q < le && *q == ':') { ++q; val = strtof(q, &nx); q = nx; }
-            out->index.push_back(idx);
-            out->value.push_back(val);
-          }
-          out->label.push_back(label);
-          out->offset.push_back(out->index.size());
-        }
+  /** append up to max_rows parsed rows to out; returns the number appended (0: the part is exhausted) */
+  size_t ReadRows(RowBlockContainer<feaid_t>* out, size_t max_rows) {
+    size_t got = 0;
+    while (got < max_rows) {
+      const char* p = buf_.data() + pos_;
+      const char* e = buf_.data() + buf_.size();
+      const char* le = p < e ? static_cast<const char*>(memchr(p, '\n', static_cast<size_t>(e - p))) : nullptr;
+      if (!le) {
+        if (next_ < end_) { Fill(); continue; }     // the line continues in the next chunk
+        if (p >= e) break;
+        le = e;                                      // last line of the part without a trailing newline
       }
-      p = le + 1;
+      got += ParseLine(p, le, out);
+      pos_ = static_cast<size_t>(le - buf_.data()) + 1;
+      if (pos_ > buf_.size()) pos_ = buf_.size();
     }
+    return got;
+  }
+  /** parse everything that is left */
+  void ParseAll(RowBlockContainer<feaid_t>* out) {
+    out->Clear();
+    while (ReadRows(out, 1u << 20)) {}
   }
 
  private:
+  void Fill() {
+    buf_.erase(0, pos_);
+    pos_ = 0;
+    const size_t n = std::min(chunk_, end_ - next_);
+    const size_t old = buf_.size();
+    buf_.resize(old + n);
+    f_.read(&buf_[old], static_cast<std::streamsize>(n));
+    next_ += n;
+  }
+  static size_t ParseLine(const char* q, const char* le, RowBlockContainer<feaid_t>* out) {
+    while (q < le && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+    if (q >= le) return 0;
+    // strtof / strtoull stop at the newline (or at the terminating NUL std::string keeps behind the last byte)
+    char* nx = nullptr;
+    const float label = strtof(q, &nx);
+    if (nx == q) return 0;
+    q = nx;
+    while (q < le) {
+      while (q < le && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+      if (q >= le) break;
+      const feaid_t idx = strtoull(q, &nx, 10);
+      if (nx == q) break;
+      q = nx;
+      float val = 1.f;
+      if (q < le && *q == ':') { ++q; val = strtof(q, &nx); q = nx; }
+      out->index.push_back(idx);
+      out->value.push_back(val);
+    }
+    out->label.push_back(label);
+    out->offset.push_back(out->index.size());
+    return 1;
+  }
+  std::ifstream f_;
   std::string buf_;
+  size_t chunk_, pos_ = 0, next_ = 0, end_ = 0;
 };
 
 /**
@@ -84,42 +112,35 @@ class LibsvmPartReader {
  * drops negative rows with probability 1 - neg_sampling (rand_r, seed 0, as the reference);
  * all-ones value arrays are dropped (:71-73).  The shuffle order uses std::mt19937 instead of the
  * reference's std::random_shuffle (whose order is implementation-defined): same distribution,
- * different permutation.
+ * different permutation.  Rows are streamed window by window (a shuffle window, or max(batch_size, 4096) rows):
+ * the file part is never held in memory as a whole.
  */
 class BatchReader {
  public:
   BatchReader(const std::string& uri, const std::string& format, unsigned part, unsigned nparts,
-              unsigned batch_size, unsigned shuffle_buf_size = 0, float neg_sampling = 1.0f, unsigned epoch = 0)
+              unsigned batch_size, unsigned shuffle_buf_size = 0, float neg_sampling = 1.0f, unsigned epoch = 0,
+              size_t chunk_bytes = 0)
       : batch_size_(batch_size), shuf_buf_(shuffle_buf_size), neg_sampling_(neg_sampling),
-        seed_(epoch * 2654435761u + part) {
-    if (format != "libsvm") throw Error("unknown format " + format + " (this build reads libsvm)");
+        seed_(epoch * 2654435761u + part), src_(Open(uri, format, part, nparts, chunk_bytes)),
+        // the reference's std::random_shuffle advances one global generator, so every epoch sees another order;
+        // here the order is a function of (epoch, part): different per epoch, reproducible per run
+        gen_(epoch * 2654435761u + part * 40503u + 1u) {
     if (shuf_buf_) DFB_CHECK(shuf_buf_ >= batch_size_);
-    LibsvmPartReader(uri, part, nparts).ParseAll(&all_);
-    order_.resize(all_.Size());
-    std::iota(order_.begin(), order_.end(), 0u);
-    if (shuf_buf_) {
-      // the reference's std::random_shuffle advances one global generator, so every epoch sees another order;
-      // here the order is a function of (epoch, part): different per epoch, reproducible per run
-      std::mt19937 gen(epoch * 2654435761u + part * 40503u + 1u);
-      for (size_t b = 0; b < order_.size(); b += shuf_buf_) {
-        const size_t e = std::min(order_.size(), b + shuf_buf_);
-        std::shuffle(order_.begin() + static_cast<std::ptrdiff_t>(b), order_.begin() + static_cast<std::ptrdiff_t>(e), gen);
-      }
-    }
   }
   bool Next() {
     batch_.Clear();
-    while (batch_.Size() < batch_size_ && cursor_ < order_.size()) {
+    while (batch_.Size() < batch_size_) {
+      if (cursor_ == order_.size() && !Refill()) break;
       const unsigned j = order_[cursor_++];
       if (shuf_buf_ != 0 || neg_sampling_ != 1.0f) {
         const float p = static_cast<float>(rand_r(&seed_)) / static_cast<float>(RAND_MAX);
-        if (neg_sampling_ < 1.0f && all_.label[j] <= 0 && p > 1 - neg_sampling_) continue;
+        if (neg_sampling_ < 1.0f && win_.label[j] <= 0 && p > 1 - neg_sampling_) continue;
       }
-      for (size_t t = all_.offset[j]; t < all_.offset[j + 1]; ++t) {
-        batch_.index.push_back(all_.index[t]);
-        batch_.value.push_back(all_.value[t]);
+      for (size_t t = win_.offset[j]; t < win_.offset[j + 1]; ++t) {
+        batch_.index.push_back(win_.index[t]);
+        batch_.value.push_back(win_.value[t]);
       }
-      batch_.label.push_back(all_.label[j]);
+      batch_.label.push_back(win_.label[j]);
       batch_.offset.push_back(batch_.index.size());
     }
     bool binary = true;
@@ -130,10 +151,28 @@ class BatchReader {
   dmlc::RowBlock<feaid_t> Value() const { return batch_.GetBlock(); }
 
  private:
+  static LibsvmPartReader Open(const std::string& uri, const std::string& format, unsigned part, unsigned nparts,
+                               size_t chunk_bytes) {
+    if (format != "libsvm") throw Error("unknown format " + format + " (this build reads libsvm)");
+    return LibsvmPartReader(uri, part, nparts, chunk_bytes);
+  }
+  // the next window of rows: exactly shuffle_buf_size rows (the last one shorter), shuffled; or the next rows in file order
+  bool Refill() {
+    win_.Clear();
+    const size_t want = shuf_buf_ ? shuf_buf_ : std::max<size_t>(batch_size_, 4096);
+    while (win_.Size() < want && src_.ReadRows(&win_, want - win_.Size())) {}
+    order_.resize(win_.Size());
+    std::iota(order_.begin(), order_.end(), 0u);
+    if (shuf_buf_) std::shuffle(order_.begin(), order_.end(), gen_);
+    cursor_ = 0;
+    return !order_.empty();
+  }
   unsigned batch_size_, shuf_buf_;
   float neg_sampling_;
   unsigned int seed_;
-  RowBlockContainer<feaid_t> all_, batch_;
+  LibsvmPartReader src_;
+  std::mt19937 gen_;
+  RowBlockContainer<feaid_t> win_, batch_;
   std::vector<unsigned> order_;
   size_t cursor_ = 0;
 };

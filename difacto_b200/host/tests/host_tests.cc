@@ -137,6 +137,33 @@ static void BatchReader_PartRead() {
   EXPECT_EQ(ttl + ttl0, 100);
 }
 
+// the part is streamed in chunks: any chunk size (here: smaller than one line, and a few lines) gives the rows of
+// the one-chunk read, for whole files and for parts, with and without a shuffle window
+static void BatchReader_StreamedChunks() {
+  for (unsigned nparts : {1u, 3u}) {
+    for (unsigned part = 0; part < nparts; ++part) {
+      for (unsigned shuf : {0u, 50u}) {
+        for (size_t chunk : {size_t(7), size_t(1000), size_t(4096)}) {
+          BatchReader whole2(DataPath(), "libsvm", part, nparts, kBatch, shuf, 1.0f, 2);
+          BatchReader piece(DataPath(), "libsvm", part, nparts, kBatch, shuf, 1.0f, 2, chunk);
+          for (;;) {
+            const bool a = whole2.Next(), b = piece.Next();
+            EXPECT_TRUE(a == b);
+            if (!a || !b) break;
+            auto x = whole2.Value(), y = piece.Value();
+            EXPECT_EQ(x.size, y.size);
+            EXPECT_EQ(x.offset[x.size], y.offset[y.size]);
+            EXPECT_TRUE(memcmp(x.index, y.index, sizeof(feaid_t) * x.offset[x.size]) == 0);
+            EXPECT_TRUE(memcmp(x.label, y.label, sizeof(real_t) * x.size) == 0);
+            EXPECT_TRUE((x.value == nullptr) == (y.value == nullptr));
+            if (x.value && y.value) EXPECT_TRUE(memcmp(x.value, y.value, sizeof(real_t) * x.offset[x.size]) == 0);
+          }
+        }
+      }
+    }
+  }
+}
+
 static void ArgParser_LastValueWins() {
   ArgParser p;
   p.AddArg("V_dim=64");
@@ -289,6 +316,7 @@ static const Case kCases[] = {
     {"Localizer.ReverseBytes", Localizer_ReverseBytes}, {"ArgParser.LastValueWins", ArgParser_LastValueWins},
     {"BatchReader.Read", BatchReader_Read}, {"BatchReader.RandRead", BatchReader_RandRead},
     {"BatchReader.PartRead", BatchReader_PartRead},
+    {"BatchReader.StreamedChunks", BatchReader_StreamedChunks},
     {"GpuFMLoss.NoV", GpuFMLoss_NoV}, {"GpuFMLoss.HasV", GpuFMLoss_HasV},
     {"GpuSGDLearner.Basic", GpuSGDLearner_Basic}, {"GpuSGDUpdater.SaveLoad", GpuSGDUpdater_SaveLoad},
     {"GpuSGDLearner.PluginCallsEqualFused", GpuSGDLearner_PluginCallsEqualFused}};

@@ -537,8 +537,11 @@ def test_full_size_training_steps_vs_oracle():
         ref = M.sgd_step(off, ids, None, lab, True, True)
         pr = E.train_step_raw(off, ids, None, lab, push_cnt=True, is_train=True)
         assert pr.nrows == ref[4] == B
-        assert abs(pr.loss - ref[0]) <= 1e-4 * abs(ref[0]), f"loss step {t}: {pr.loss} vs {ref[0]}"
-        assert abs(pr.penalty - ref[1]) <= 1e-4 * abs(ref[1]) + 1e-5, f"penalty step {t}: {pr.penalty} vs {ref[1]}"
+        # the reference sums the 65536 row losses (and the penalty terms) sequentially in float32 (loss.h:57-66,
+        # sgd_learner.cc:249-273): at this size that running sum itself is only good to a few 1e-4 relative (step 0, an
+        # empty model: exactly 65536 ln 2 = 45426.1 here, 45437.3 there); the engine accumulates in double
+        assert abs(pr.loss - ref[0]) <= 1e-3 * abs(ref[0]), f"loss step {t}: {pr.loss} vs {ref[0]}"
+        assert abs(pr.penalty - ref[1]) <= 1e-3 * abs(ref[1]) + 1e-5, f"penalty step {t}: {pr.penalty} vs {ref[1]}"
         seen.append(ids)
     assert E.table_stats()["n_keys"] == M.size()
     assert E.rng_state() == M.seed()

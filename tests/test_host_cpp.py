@@ -38,6 +38,7 @@ def test_host_unit_cases_cpu(host_bin, libsvm_fixture):
     out = subprocess.run([os.path.join(host_bin, "host_tests"), "-Gpu"], env=env, capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Localizer.Base" in out.stdout and "BatchReader.PartRead" in out.stdout and "0 failed" in out.stdout
+    assert "BatchReader.StreamedChunks" in out.stdout
 
 
 def test_cli_conf_surface(host_bin, tmp_path, libsvm_fixture):
