@@ -473,17 +473,14 @@ def parity_check(rank, world, local_rank, V_dim, steps=4, B=512, nnz_row=24, ids
             "ok": bool(flag_mismatch == 0 and fail == 0 and loss_rel < 1e-4)}
 
 
-def bench_main(args, rank, world, local_rank, benchmod):
-    import json
+def _measure(args, rank, world, local_rank, benchmod, sampler=None, with_e2e=True):
+    """one configuration on `world` GPUs: engines, the NVLink-sharded store, table warm-up, the timed region
+    (device-timed, max over ranks), the per-phase timings and (optionally) the end-to-end region"""
     from difacto_b200 import capi
-
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     kw = benchmod.hyper(args)
     nb = args.working_set
-    nnz_row = args.nnz if args.workload == "synthetic" else 39
+    nnz_row = benchmod.nnz_of(args)
     B, k = args.batch, args.vdim
     N = B * nnz_row
     steps, warm = args.steps, args.warmup
@@ -518,8 +515,7 @@ def bench_main(args, rank, world, local_rank, benchmod):
     dist.barrier()
     torch.cuda.synchronize()
     launches0 = E.launch_count()
-    sampler = benchmod.ClockSampler(local_rank)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     wall0 = time.time()
     E.time_mark(0)
@@ -549,7 +545,7 @@ def bench_main(args, rank, world, local_rank, benchmod):
 
     # ---- e2e: raw uint64 CSR from pinned host memory every step + Progress read back ----
     e2e = None
-    if not args.no_e2e:
+    if with_e2e and not args.no_e2e:
         def run_e2e(nsteps, first):
             loss = 0.0
             for t in range(nsteps):
@@ -580,10 +576,27 @@ def bench_main(args, rank, world, local_rank, benchmod):
                "api": "dfb_shard_step_async (+ dfb_prefetch_raw) + dfb_wait_step per rank: raw uint64 CSR from pinned host "
                       "memory, Localizer::Compact on the GPU, NVLink-sharded fused step; no NCCL call and no host "
                       "synchronisation inside a step"}
+    wall_end = time.time()       # timed region + phase profile + e2e region: the GPU is under load throughout
     st_tab = E.table_stats()
     loss_all = torch.tensor([prog.loss, prog.nrows], device=dev, dtype=torch.float64)
     dist.all_reduce(loss_all)
     E.close()
+    return dict(ms=ms, launches=launches, phases=phases, e2e=e2e, st_tab=st_tab, loss_all=loss_all, U0=U0, wall0=wall0, wall1=wall_end,
+                B=B, k=k, N=N, nb=nb, steps=steps, warm=warm)
+
+
+def bench_main(args, rank, world, local_rank, benchmod):
+    import json
+    from difacto_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sampler = benchmod.ClockSampler(local_rank) if rank == 0 else None
+    r = _measure(args, rank, world, local_rank, benchmod, sampler=sampler)
+    ms, launches, phases, e2e, st_tab, loss_all = r["ms"], r["launches"], r["phases"], r["e2e"], r["st_tab"], r["loss_all"]
+    U0, wall0, B, k, N, nb, steps, warm = r["U0"], r["wall0"], r["B"], r["k"], r["N"], r["nb"], r["steps"], r["warm"]
     parity = None
     try:
         parity = parity_check(rank, world, local_rank, k)
@@ -593,10 +606,11 @@ def bench_main(args, rank, world, local_rank, benchmod):
         sampler.stop()
         peak, peak_src = benchmod.load_peaks()
         fwd, emit, upd, step_model = benchmod.byte_model(B, N, U0, k)
-        # what crosses NVLink per GPU and direction per step: the slices of the batch's structure, the partial sums
+        # what crosses NVLink per GPU and direction per step: the slices of the batch's structure (per nnz: 8-byte
+        # (row, x) payload + 4-byte key index + 4-byte x; every batch is valued on the wire), the partial sums
         # ((k+2) floats per row and owner) one way, p and p*XV ((k+1) floats per row and owner) the other way
         fr = (world - 1) / world
-        nvl_out = fr * (U0 * 12 + N * 8) + (world - 1) * B * (k + 2) * 4 + (world - 1) * B * (k + 1) * 4
+        nvl_out = fr * (U0 * 12 + N * 16) + (world - 1) * B * (k + 2) * 4 + (world - 1) * B * (k + 1) * 4
         rows_model = 2 * U0 * fr * (8 + 4 * (k + 1))       # rows of the active keys, pull + push
         nvl = 770.0   # measured peer copy GB/s per direction (B200_PROFILING.md)
         upd_ms = phases["shard_owner_updates"]
@@ -623,9 +637,45 @@ def bench_main(args, rank, world, local_rank, benchmod):
                                     "note": "the step is HBM-bound again: the rows stay on their owner; the row-exchange "
                                             "protocol of round 1 would move rows_exchange_model_bytes per direction"}},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(wall0, time.time()), "loss_per_example": float(loss_all[0] / max(loss_all[1], 1)),
+            "clocks": sampler.summary(wall0, r["wall1"]), "loss_per_example": float(loss_all[0] / max(loss_all[1], 1)),
             "phases_ms_per_step_rank0": phases, "phases_sum_ms": float(sum(phases.values())), "parity": parity,
         }
+    # the Criteo-shaped configurations BASELINE.json names, one short run each on the same ranks.  The headline line
+    # is complete at this point: a watchdog prints it and ends the process if a sweep point should ever stall (a
+    # rank failing on its own would leave the others waiting in a collective), so the sweep cannot cost the number
+    import threading
+
+    def bail():
+        if rank == 0:
+            line["sweep"] = {"error": "sweep did not finish within its time limit; headline unaffected"}
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    dog = threading.Timer(150.0, bail)
+    dog.daemon = True
+    dog.start()
+    sweep = None
+    if not args.no_sweep and args.workload == "synthetic":
+        import argparse
+        sweep = {}
+        for name, over in (("criteo39_V64_conf", dict(workload="criteo39", vdim=64, hyper="criteo_conf")),
+                           ("criteo39_V32_ftrl_l1", dict(workload="criteo39", vdim=32, hyper="ftrl_l1"))):
+            a2 = argparse.Namespace(**vars(args))
+            a2.steps, a2.warmup, a2.working_set = 6, 3, 4
+            for k_, v_ in over.items():
+                setattr(a2, k_, v_)
+            try:
+                r2 = _measure(a2, rank, world, local_rank, benchmod, with_e2e=False)
+                sweep[name] = {"value": r2["steps"] * r2["B"] * world / (r2["ms"] * 1e-3), "unit": "examples/s",
+                               "ms_per_step": r2["ms"] / r2["steps"], "steps": r2["steps"], "warmup": r2["warm"],
+                               "unique_keys_per_batch": int(r2["U0"]), "hyper": benchmod.hyper(a2), "V_dim": a2.vdim,
+                               "phases_ms_per_step_rank0": r2["phases"],
+                               "loss_per_example": float(r2["loss_all"][0] / max(float(r2["loss_all"][1]), 1.0))}
+            except Exception as e:      # a sweep point must not take the headline down
+                sweep[name] = {"error": repr(e)}
+    dog.cancel()
+    if rank == 0:
+        line["sweep"] = sweep
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize()
     dist.barrier()
