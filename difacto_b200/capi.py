@@ -36,7 +36,7 @@ EXPORTS = [
     "dfb_dev_fm_step_peer", "dfb_localize", "dfb_train_step_raw", "dfb_train_step_raw_async",
     "dfb_train_step_raw_dev", "dfb_prefetch_raw", "dfb_snapshot_size", "dfb_snapshot", "dfb_restore",
     "dfb_shard_init", "dfb_shard_export", "dfb_shard_connect", "dfb_shard_step_dev", "dfb_shard_step_async",
-    "dfb_shard_info", "dfb_shard_begin_async", "dfb_shard_phase", "dfb_time_mark", "dfb_time_elapsed_ms",
+    "dfb_shard_info", "dfb_shard_begin_async", "dfb_shard_begin_dev", "dfb_shard_phase", "dfb_time_mark", "dfb_time_elapsed_ms",
 ]
 
 _LIB = None
@@ -108,6 +108,7 @@ def lib():
         L.dfb_time_mark.argtypes = [vp, C.c_int]
         L.dfb_time_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.dfb_shard_begin_async.argtypes = [vp, sz, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.dfb_shard_begin_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, C.c_int, C.c_int]
         L.dfb_shard_phase.argtypes = [vp, C.c_int]
         L.dfb_shard_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(sz), C.POINTER(sz),
                                      C.POINTER(u64)]
@@ -439,6 +440,10 @@ class Engine:
     def shard_begin_async(self, nrows, offset, ids, value, label, push_cnt=False, is_train=True):
         self._ck(self.L.dfb_shard_begin_async(self.h, nrows, _p(offset), _p(ids), _p(value), _p(label),
                                               int(push_cnt), int(is_train)))
+
+    def shard_begin_dev(self, nrows, nnz, d_offset, d_ids, d_value, d_label, push_cnt=False, is_train=True):
+        self._ck(self.L.dfb_shard_begin_dev(self.h, nrows, nnz, _p(d_offset), _p(d_ids), _p(d_value), _p(d_label),
+                                            int(push_cnt), int(is_train)))
 
     def shard_phase(self, phase):
         self._ck(self.L.dfb_shard_phase(self.h, int(phase)))

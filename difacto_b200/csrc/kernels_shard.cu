@@ -65,20 +65,23 @@ __global__ void k_shard_signal(SignalDst d, unsigned long long value) {
 __global__ void k_shard_bounds(const uint64_t* __restrict__ keys, const unsigned long long* __restrict__ dU,
                                size_t U_cap, const int* __restrict__ col_start, size_t nnz, int S, size_t Kseg,
                                size_t Nseg, ShardBounds* wb, DevProgress* prog) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   const size_t U = dev_count(U_cap, dU);
   const uint64_t width = ~0ULL / (uint64_t)S;     // postoffice.cc:130-134
-  ShardBounds b;
-  b.kb[0] = 0;
-  for (int s = 1; s < S; ++s) {
-    const uint64_t lo_key = width * (uint64_t)s;
-    size_t lo = (size_t)b.kb[s - 1], hi = U;
-    while (lo < hi) {
+  // lane s finds the first key of owner s: S - 1 independent binary searches side by side
+  const int lane = threadIdx.x;
+  size_t lo = 0, hi = (lane >= 1 && lane < S) ? U : 0;
+  const uint64_t lo_key = width * (uint64_t)lane;
+  while (__any_sync(kFullMask, lo < hi)) {
+    if (lo < hi) {
       const size_t mid = lo + (hi - lo) / 2;
       if (keys[mid] < lo_key) lo = mid + 1; else hi = mid;
     }
-    b.kb[s] = (int)lo;
   }
+  ShardBounds b;
+  for (int s = 0; s < S; ++s) b.kb[s] = (int)__shfl_sync(kFullMask, (unsigned long long)lo, s);
+  if (lane != 0) return;
+  b.kb[0] = 0;
   b.kb[S] = (int)U;
   for (int s = 0; s <= S; ++s) b.nb[s] = (U == 0) ? 0 : ((size_t)b.kb[s] < U ? col_start[b.kb[s]] : (int)nnz);
   b.valid = U > 0 ? 1 : 0;
@@ -327,27 +330,24 @@ __global__ void __launch_bounds__(256) k_shard_reduce(ReduceArgs a) {
 // ------------------------------------------------------------------------------------------------------
 // owner side
 // ------------------------------------------------------------------------------------------------------
-// model_[key] for the key segment ONE worker sent (SGDUpdater::Get, sgd_updater.cc:32-56); the owner runs it once
-// per worker, in rank order.  With stamp != 0 every touched entry also records which workers hold it in this
-// step (entry.pad = stamp << 8 | worker bitmask).  A key that a lower-rank worker also holds will already have
-// been updated by that worker's push when this worker's push is applied, but the gradient a worker pushes is
-// taken at the V it pulled (fm_loss.h:181-188): such keys are flagged (conf) and their pull-time V row is saved
-// here, while the entry is at hand (warp-cooperative copy).
+// model_[key] for the key segment ONE worker sent (SGDUpdater::Get, sgd_updater.cc:32-56): slots only (find or
+// default-construct); the owner runs it once per worker, in rank order, on its lookup stream -- beside the previous
+// step's update, which addresses entries by slot and is not disturbed by inserts.  With stamp != 0 every touched
+// entry also records which workers hold it in this step (entry.pad = stamp << 8 | worker bitmask).  A key that a
+// lower-rank worker also holds will already have been updated by that worker's push when this worker's push is
+// applied, but the gradient a worker pushes is taken at the V it pulled (fm_loss.h:181-188): such keys are
+// flagged (conf); k_shard_pull saves their pull-time V row.
 template <bool INSERT>
-__global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a, int r, unsigned char* __restrict__ conf,
-                                                      float* __restrict__ vsave, int K) {
+__global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a, int r, unsigned char* __restrict__ conf) {
   constexpr int ILP = 2;
   const size_t n = (size_t)a.hdr[r]->nkeys < a.Kseg ? (size_t)a.hdr[r]->nkeys : a.Kseg;
   const uint64_t* __restrict__ keys = a.keys[r];
   const size_t o = (size_t)r * a.Kseg;
-  const int lane = threadIdx.x & 31;
   const size_t tile = (size_t)blockDim.x * ILP;
-  const size_t npad = (n + tile - 1) / tile * tile;
-  for (size_t base = (size_t)blockIdx.x * tile; base < npad; base += (size_t)gridDim.x * tile) {
+  for (size_t base = (size_t)blockIdx.x * tile; base < n; base += (size_t)gridDim.x * tile) {
     unsigned long long key[ILP];
     uint64_t h[ILP];
     Entry256 e[ILP];
-    int vr_q[ILP], cf_q[ILP];
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
       const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
@@ -362,79 +362,69 @@ __global__ void __launch_bounds__(256) k_shard_lookup(Table t, LookupArgs a, int
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
       const size_t i = base + (size_t)q * blockDim.x + threadIdx.x;
-      vr_q[q] = -1; cf_q[q] = 0;
       if (i >= n) continue;
-      int slot = -1, vr = -1;
-      float w = 0.f;
+      int slot = -1, old = 0;
       if (key[q] == kEmptyKey) {
         raise_err(t.prog, DFB_ERR_INVALID);
       } else if (e[q].key == key[q]) {
-        slot = (int)h[q]; w = e[q].w(); vr = e[q].vrow();
+        slot = (int)h[q]; old = (int)(unsigned)(e[q].q1 >> 32);
       } else {
         slot = table_find<INSERT>(t, key[q], h[q]);
-        if (slot >= 0) { w = t.tab[slot].w; vr = t.tab[slot].vrow; }
+        if (slot >= 0) old = *reinterpret_cast<volatile int*>(&t.tab[slot].pad);
       }
       const size_t v = o + i;
       a.slot[v] = slot;
-      a.w[v] = w;
-      a.vrow[v] = vr;
-      a.wv[v] = make_int2(__float_as_int(w), vr);
       if (a.stamp != 0) {
+        // the keys of one worker are distinct and the workers' lookups are separate launches in rank order, so the
+        // stamp word of an entry has one writer at a time: plain read (it came with the entry) - modify - write
         int c = 0;
         if (slot >= 0) {
-          int* pad = &t.tab[slot].pad;
-          int old = *reinterpret_cast<volatile int*>(pad);
-          for (;;) {
-            const bool cur = (((unsigned)old) >> 8) == a.stamp;
-            const int fresh = (cur ? old : (int)(a.stamp << 8)) | (1 << r);
-            const int prev = atomicCAS(pad, old, fresh);
-            if (prev == old) { c = (cur && (old & ((1 << r) - 1) & 0xff) != 0) ? 1 : 0; break; }
-            old = prev;
-          }
+          const bool cur = (((unsigned)old) >> 8) == a.stamp;
+          t.tab[slot].pad = (cur ? old : (int)(a.stamp << 8)) | (1 << r);
+          c = (cur && (old & ((1 << r) - 1) & 0xff) != 0) ? 1 : 0;
         }
         conf[v] = (unsigned char)c;
-        cf_q[q] = c; vr_q[q] = vr;
-      }
-    }
-    if (a.stamp != 0) {
-#pragma unroll
-      for (int q = 0; q < ILP; ++q) {
-        unsigned m = __ballot_sync(kFullMask, cf_q[q] != 0 && vr_q[q] >= 0);
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          const int vrb = __shfl_sync(kFullMask, vr_q[q], b);
-          const size_t ib = base + (size_t)q * blockDim.x + (threadIdx.x - lane) + b;
-          const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vrb * t.rs);
-          float4* dst = reinterpret_cast<float4*>(vsave + (o + ib) * (size_t)K);
-          for (int l = lane; l < K / 4; l += 32) dst[l] = src[l];
-        }
       }
     }
   }
 }
 
-// feature-count steps: Update(kFeaCount) may allocate V rows between the lookup and the Pull, so the pull-time rows
-// of the flagged keys are saved again from the refreshed view
-__global__ void __launch_bounds__(256) k_shard_save_conf(Table t, LookupArgs a, const unsigned char* __restrict__ conf,
-                                                         float* __restrict__ vsave, int K) {
+// Pull (Store::Pull -> SGDUpdater::Get, sgd_updater.cc:41-62) of all workers' key segments at once: {w, V-row index} of
+// every resolved slot -- taken AFTER the previous step's updates and this step's Update(kFeaCount), while the slots
+// themselves were resolved earlier (k_shard_lookup runs beside the previous step's update: open addressing without
+// deletes keeps slots stable).  For a key a lower-rank worker of this step holds too (conf), the pull-time V row is
+// saved: that worker's push will have changed the table row by the time this worker's gradient needs it.
+__global__ void __launch_bounds__(256) k_shard_pull(Table t, LookupArgs a, const unsigned char* __restrict__ conf,
+                                                    float* __restrict__ vsave, int K) {
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   const size_t total = (size_t)a.S * a.Kseg;
   for (size_t base = warp0 * 32; base < total; base += nwarps * 32) {
     const size_t v = base + lane;
-    int vr = -1;
+    int vr_save = -1;
     if (v < total) {
       const int r = (int)(v / a.Kseg);
       const size_t i = v - (size_t)r * a.Kseg;
-      if (i < (size_t)a.hdr[r]->nkeys && conf[v]) vr = a.vrow[v];
+      if (i < (size_t)a.hdr[r]->nkeys) {
+        const int s = a.slot[v];
+        float w = 0.f;
+        int vr = -1;
+        if (s >= 0) {
+          const Entry256 e = load_entry(&t.tab[s]);
+          w = e.w(); vr = e.vrow();
+        }
+        a.w[v] = w;
+        a.vrow[v] = vr;
+        a.wv[v] = make_int2(__float_as_int(w), vr);
+        if (a.stamp != 0 && conf[v]) vr_save = vr;
+      }
     }
-    unsigned m = __ballot_sync(kFullMask, vr >= 0);
+    unsigned m = __ballot_sync(kFullMask, vr_save >= 0);
     while (m) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      const int vrb = __shfl_sync(kFullMask, vr, b);
+      const int vrb = __shfl_sync(kFullMask, vr_save, b);
       const float4* src = reinterpret_cast<const float4*>(t.V + (size_t)vrb * t.rs);
       float4* dst = reinterpret_cast<float4*>(vsave + (base + b) * (size_t)K);
       for (int l = lane; l < K / 4; l += 32) dst[l] = src[l];
@@ -539,17 +529,16 @@ int launch_shard_reduce(int V_dim, const ReduceArgs& a, cudaStream_t s) {
   return -1;
 }
 
-int launch_shard_lookup(Table& t, const LookupArgs& a, int r, bool insert, unsigned char* conf, float* vsave, int K,
-                        cudaStream_t s) {
+int launch_shard_lookup(Table& t, const LookupArgs& a, int r, bool insert, unsigned char* conf, cudaStream_t s) {
   const int grid = grid_cap(a.Kseg, 256 * 2, 148 * 64);
-  if (insert) k_shard_lookup<true><<<grid, 256, 0, s>>>(t, a, r, conf, vsave, K);
-  else        k_shard_lookup<false><<<grid, 256, 0, s>>>(t, a, r, conf, vsave, K);
+  if (insert) k_shard_lookup<true><<<grid, 256, 0, s>>>(t, a, r, conf);
+  else        k_shard_lookup<false><<<grid, 256, 0, s>>>(t, a, r, conf);
   return 1;
 }
 
-int launch_shard_save_conf(Table& t, const LookupArgs& a, const unsigned char* conf, float* vsave, int K, cudaStream_t s) {
+int launch_shard_pull(Table& t, const LookupArgs& a, const unsigned char* conf, float* vsave, int K, cudaStream_t s) {
   const size_t total = (size_t)a.S * a.Kseg;
-  k_shard_save_conf<<<grid_cap((total + 31) / 32, 8, 148 * 8), 256, 0, s>>>(t, a, conf, vsave, K);
+  k_shard_pull<<<grid_cap((total + 31) / 32, 8, 148 * 16), 256, 0, s>>>(t, a, conf, vsave, K);
   return 1;
 }
 

@@ -8,9 +8,9 @@
 // for what crosses NVLink.  One step of every rank, all asynchronous, no host synchronisation:
 //
 //   stream W (worker)            stream O (owner = the engine's main stream)            stream F (finish)
-//   localize raw ids (GPU)
-//   segment bounds, scatter the
-//   CSC/CSR slices -> owners  --struct-->  lookup(+feacnt) of all workers' key segments
+//   localize raw ids (GPU)                 [stream L: slots of all workers' key segments (find / insert), beside
+//   segment bounds, scatter the             the update of the previous step]
+//   CSC/CSR slices -> owners  --struct-->  (feacnt,) pull {w, V row} of all workers' key segments
 //                                          partial interaction sums of all workers' rows
 //   add partials, pred/loss/p <--part----  (stored into the workers' mailboxes)
 //   p, p*XV -> owners         --pxv----->  per worker, rank order: per-key gradient from its
@@ -37,12 +37,14 @@ struct ShardState {
   void* mailbox = nullptr;
   void* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool connected = false;
-  cudaStream_t w_stream = nullptr, f_stream = nullptr;
-  cudaEvent_t ev_struct[2] = {}, ev_part[2] = {}, ev_reduce[2] = {}, ev_auc[2] = {}, ev_upd[2] = {}, ev_fin[2] = {};
+  cudaStream_t w_stream = nullptr, f_stream = nullptr, l_stream = nullptr;
+  cudaEvent_t ev_struct[2] = {}, ev_part[2] = {}, ev_reduce[2] = {}, ev_auc[2] = {}, ev_upd[2] = {}, ev_fin[2] = {},
+              ev_lookup[2] = {};
   uint64_t step = 0;
   dfb_engine::LocSet L;
   DevBuf wb, rowcnt, pred[2];
-  DevBuf slot, w, vrow, wv, conf, vsave, flags, ws;
+  DevBuf slot[2], conf[2];        // by step parity: the lookup of step t+1 runs beside the update of step t
+  DevBuf w, vrow, wv, vsave, flags, ws;
   DevProgress* dprog = nullptr;   // device: [0,S) per-worker scratch, [S,S+2) worker Progress by parity, [S+2,S+4) staging
   long long timeout_cycles = 0;
   // the step being enqueued (dfb_shard_begin_* .. dfb_shard_phase(4))
@@ -124,7 +126,7 @@ int shard_phase(dfb_engine* h, int phase) {
   const unsigned long long fv = t + 1;
   const bool valued = d_val != nullptr;      // of THIS rank's batch; on the wire every batch is valued (kernels_shard.cu)
   const unsigned remote = ((1u << S) - 1u) & ~(1u << me);
-  cudaStream_t W = sh.w_stream, O = h->stream, A = h->aux_stream, F = sh.f_stream;
+  cudaStream_t W = sh.w_stream, O = h->stream, A = h->aux_stream, F = sh.f_stream, L = sh.l_stream;
   void* mine = sh.mailbox;
   const size_t Kseg = lay.Kseg;
 
@@ -189,33 +191,38 @@ int shard_phase(dfb_engine* h, int phase) {
   }
 
   if (phase == 1) {
-  // ------------------------------- O part 1: lookup, partial interaction sums -------------------------------
-  DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_struct[d], 0));
-  h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_STRUCT, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, O);
-  StageTimer tm_fwd(h, 7, O);
+  // ------------------------------- O part 1: lookup, pull, partial interaction sums -------------------------------
+  // (a) stream L: the slots of all workers' key segments (find / insert) and which keys several workers share --
+  // needs only the workers' structure, so it runs beside the update of the previous step on stream O
+  DFB_CUDA(h, cudaStreamWaitEvent(L, sh.ev_struct[d], 0));
+  if (t >= 2) DFB_CUDA(h, cudaStreamWaitEvent(L, sh.ev_fin[d], 0));        // slot[d] / conf[d] of step t-2 are free
+  h->launches += launch_shard_wait(lay.flag(mine, ShardLayout::F_STRUCT, 0), 8, remote, fv, sh.timeout_cycles, h->tab.prog, L);
   memset(&la, 0, sizeof(la));
   la.S = S; la.Kseg = Kseg;
   la.stamp = (is_train && S > 1) ? (unsigned)((fv & 0xFFFFFFULL) ? (fv & 0xFFFFFFULL) : 1ULL) : 0u;
-  la.slot = sh.slot.as<int>(); la.w = sh.w.as<float>(); la.vrow = sh.vrow.as<int>(); la.wv = sh.wv.as<int2>();
+  la.slot = sh.slot[d].as<int>(); la.w = sh.w.as<float>(); la.vrow = sh.vrow.as<int>(); la.wv = sh.wv.as<int2>();
   for (int r = 0; r < S; ++r) {
     la.hdr[r] = hdr[r];
     la.keys[r] = lay.at<uint64_t>(mine, lay.off_keys, lay.str_keys, d, r);
   }
-  // a validation / prediction batch must not grow the table (a missing entry reads as w = 0, no V)
-  for (int r = 0; r < S; ++r)
-    h->launches += launch_shard_lookup(h->tab, la, r, is_train || push_cnt, sh.conf.as<unsigned char>(),
-                                       sh.vsave.as<float>(), K, O);
+  {
+    StageTimer tm_lk(h, 0, L);
+    // a validation / prediction batch must not grow the table (a missing entry reads as w = 0, no V)
+    for (int r = 0; r < S; ++r)
+      h->launches += launch_shard_lookup(h->tab, la, r, is_train || push_cnt, sh.conf[d].as<unsigned char>(), L);
+  }
+  DFB_CUDA(h, cudaEventRecord(sh.ev_lookup[d], L));
   DFB_DBG(h, "lookup");
+  // (b) stream O, after the previous step's update: Push(kFeaCount) before Pull (sgd_learner.cc:214-217; one Update
+  // per worker, rank order), the Pull itself, the partial sums
+  DFB_CUDA(h, cudaStreamWaitEvent(O, sh.ev_lookup[d], 0));
+  StageTimer tm_fwd(h, 7, O);
   if (push_cnt) {
-    // Push(kFeaCount) before Pull (sgd_learner.cc:214-217): one Update per worker, rank order
     for (int r = 0; r < S; ++r)
       h->launches += launch_feacnt(h->tab, h->prm, la.slot + (size_t)r * Kseg, Kseg, &hdr[r]->nkeys, nullptr,
                                    lay.at<int>(mine, lay.off_cstart, lay.str_cstart, d, r), flags, ws, O);
-    for (int r = 0; r < S; ++r)
-      h->launches += launch_pull_view(h->tab, la.slot + (size_t)r * Kseg, Kseg, &hdr[r]->nkeys, la.w + (size_t)r * Kseg,
-                                      la.vrow + (size_t)r * Kseg, la.wv + (size_t)r * Kseg, O);
-    if (la.stamp) h->launches += launch_shard_save_conf(h->tab, la, sh.conf.as<unsigned char>(), sh.vsave.as<float>(), K, O);
   }
+  h->launches += launch_shard_pull(h->tab, la, sh.conf[d].as<unsigned char>(), sh.vsave.as<float>(), K, O);
   DFB_DBG(h, "feacnt / pull view");
   {
     PartArgs pa;
@@ -306,7 +313,7 @@ int shard_phase(dfb_engine* h, int phase) {
       tt.prog = sh.src_prog(r);
       ShardApply ap;
       ap.w_pulled = la.w + o;
-      ap.conf = la.stamp ? sh.conf.as<unsigned char>() + o : nullptr;
+      ap.conf = la.stamp ? sh.conf[d].as<unsigned char>() + o : nullptr;
       ap.vsave = sh.vsave.as<float>() + o * (size_t)K;
       const void* occ_r = lay.at<void>(mine, lay.off_occ, lay.str_occ, d, r);
       const float* p_r = lay.at<float>(mine, lay.off_p, lay.str_p, d, r);
@@ -380,10 +387,12 @@ void dfbh::shard_destroy(dfb_engine* h) {
   if (!sh) return;
   if (sh->w_stream) cudaStreamDestroy(sh->w_stream);
   if (sh->f_stream) cudaStreamDestroy(sh->f_stream);
-  cudaEvent_t* evs[] = {sh->ev_struct, sh->ev_part, sh->ev_reduce, sh->ev_auc, sh->ev_upd, sh->ev_fin};
+  if (sh->l_stream) cudaStreamDestroy(sh->l_stream);
+  cudaEvent_t* evs[] = {sh->ev_struct, sh->ev_part, sh->ev_reduce, sh->ev_auc, sh->ev_upd, sh->ev_fin, sh->ev_lookup};
   for (auto* e : evs) for (int i = 0; i < 2; ++i) if (e[i]) cudaEventDestroy(e[i]);
   DevBuf* bufs[] = {&sh->L.keys, &sh->L.lidx, &sh->L.cnt, &sh->L.occ_sorted, &sh->L.col_start, &sh->L.col_end, &sh->L.scal,
-                    &sh->wb, &sh->rowcnt, &sh->pred[0], &sh->pred[1], &sh->slot, &sh->w, &sh->vrow, &sh->wv, &sh->conf,
+                    &sh->wb, &sh->rowcnt, &sh->pred[0], &sh->pred[1], &sh->slot[0], &sh->slot[1], &sh->w, &sh->vrow, &sh->wv, &sh->conf[0],
+                    &sh->conf[1],
                     &sh->vsave, &sh->flags, &sh->ws};
   for (auto* b : bufs) if (b->p) cudaFree(b->p);
   if (sh->dprog) cudaFree(sh->dprog);
@@ -396,6 +405,7 @@ int dfbh::shard_sync(dfb_engine* h) {
   ShardState* sh = h->shard;
   if (!sh) return DFB_OK;
   DFB_CUDA(h, cudaStreamSynchronize(sh->w_stream));
+  DFB_CUDA(h, cudaStreamSynchronize(sh->l_stream));
   DFB_CUDA(h, cudaStreamSynchronize(h->aux_stream));
   DFB_CUDA(h, cudaStreamSynchronize(h->stream));
   DFB_CUDA(h, cudaStreamSynchronize(sh->f_stream));
@@ -432,17 +442,20 @@ int dfb_shard_init(dfb_handle h, int rank, int nranks, size_t max_rows, size_t m
   sh->peer[rank] = sh->mailbox;
   if ((e = cudaStreamCreateWithFlags(&sh->w_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
   if ((e = cudaStreamCreateWithFlags(&sh->f_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
-  cudaEvent_t* evs[] = {sh->ev_struct, sh->ev_part, sh->ev_reduce, sh->ev_auc, sh->ev_upd, sh->ev_fin};
+  if ((e = cudaStreamCreateWithFlags(&sh->l_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
+  cudaEvent_t* evs[] = {sh->ev_struct, sh->ev_part, sh->ev_reduce, sh->ev_auc, sh->ev_upd, sh->ev_fin, sh->ev_lookup};
   for (auto* ev : evs)
     for (int i = 0; i < 2; ++i)
       if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaEventCreate"));
   const size_t tot = (size_t)nranks * Kseg;
   int rc = 0;
-  if ((rc = h->ensure(sh->wb, sizeof(ShardBounds))) || (rc = h->ensure(sh->slot, tot * 4)) || (rc = h->ensure(sh->w, tot * 4)) ||
+  if ((rc = h->ensure(sh->wb, sizeof(ShardBounds))) || (rc = h->ensure(sh->slot[0], tot * 4)) || (rc = h->ensure(sh->slot[1], tot * 4)) || (rc = h->ensure(sh->w, tot * 4)) ||
       (rc = h->ensure(sh->vrow, tot * 4)) || (rc = h->ensure(sh->wv, tot * 8)) || (rc = h->ensure(sh->flags, tot * 4)) ||
       (rc = h->ensure(sh->ws, (tot / 32 + 64) * 4)))
     return fail(rc);
-  if (nranks > 1 && ((rc = h->ensure(sh->conf, tot)) || (rc = h->ensure(sh->vsave, tot * (size_t)K * 4)))) return fail(rc);
+  if (nranks > 1 && ((rc = h->ensure(sh->conf[0], tot)) || (rc = h->ensure(sh->conf[1], tot)) ||
+                     (rc = h->ensure(sh->vsave, tot * (size_t)K * 4))))
+    return fail(rc);
   // Every workspace a step can touch is allocated NOW, for the declared capacities: a cudaMalloc / cudaFree in the
   // middle of a step is not just slow -- with peer access enabled it synchronises the peer devices, whose pollers
   // may be waiting for the very step this rank has not finished enqueuing (ranks that are threads of one process).
@@ -535,6 +548,13 @@ int dfb_shard_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, con
                       in.lab.as<float>(), push_cnt, is_train, in.copied, in.consumed);
   h->seq++;
   return rc;
+}
+
+int dfb_shard_begin_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint64_t* d_ids,
+                        const float* d_value_or_null, const float* d_label, int push_cnt, int is_train) {
+  if (!h) return DFB_ERR_INVALID;
+  DFB_CUDA(h, cudaSetDevice(h->device));
+  return shard_begin(h, nrows, nnz, d_offset, d_ids, d_value_or_null, d_label, push_cnt, is_train, nullptr, nullptr);
 }
 
 int dfb_shard_begin_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids, const float* value,

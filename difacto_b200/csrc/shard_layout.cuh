@@ -120,9 +120,8 @@ int launch_shard_subcsr(const uint64_t* offset, const uint32_t* lidx, const floa
                         cudaStream_t s);
 int launch_shard_reduce(int V_dim, const ReduceArgs& a, cudaStream_t s);
 // one launch per worker, in rank order (conf / vsave: [S][Kseg] flags and [S][Kseg][K] saved rows; unused when stamp == 0)
-int launch_shard_lookup(Table& t, const LookupArgs& a, int r, bool insert, unsigned char* conf, float* vsave, int K,
-                        cudaStream_t s);
-int launch_shard_save_conf(Table& t, const LookupArgs& a, const unsigned char* conf, float* vsave, int K, cudaStream_t s);
+int launch_shard_lookup(Table& t, const LookupArgs& a, int r, bool insert, unsigned char* conf, cudaStream_t s);
+int launch_shard_pull(Table& t, const LookupArgs& a, const unsigned char* conf, float* vsave, int K, cudaStream_t s);
 int launch_shard_done(DevProgress* src_prog, DevProgress* main_prog, double* pen_dst, unsigned long long* flag_dst,
                       unsigned long long value, cudaStream_t s);
 int launch_shard_collect(const double* pen_in, int stride_f64, int S, DevProgress* prog_w, DevProgress* main_prog,

@@ -348,6 +348,8 @@ int dfb_shard_step_async(dfb_handle h, size_t nrows, const uint64_t* offset, con
  * binary, valued and empty minibatches. */
 int dfb_shard_begin_async(dfb_handle h, size_t nrows, const uint64_t* offset, const uint64_t* ids,
                           const float* value_or_null, const float* label, int push_cnt, int is_train);
+int dfb_shard_begin_dev(dfb_handle h, size_t nrows, size_t nnz, const uint64_t* d_offset, const uint64_t* d_ids,
+                        const float* d_value_or_null, const float* d_label, int push_cnt, int is_train);
 int dfb_shard_phase(dfb_handle h, int phase);
 int dfb_shard_info(dfb_handle h, int* rank, int* nranks, size_t* seg_keys, size_t* seg_nnz, uint64_t* steps);
 
