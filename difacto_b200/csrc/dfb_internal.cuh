@@ -189,7 +189,7 @@ int launch_grad_finalize_dense(int V_dim, int ks, size_t nkeys, const int* hasv,
                                const float* xxp, float* gV, cudaStream_t s);
 
 // ---- launchers (kernels_table.cu) ----
-extern int g_lookup_ilp, g_lookup_ctas;
+extern int g_lookup_ilp, g_lookup_ctas, g_update_persistent;
 int launch_table_init(Table& t, unsigned seed, cudaStream_t s);
 // find (or insert) keys; slot_out[i] = hash position or -1.  When pull outputs are non-null also
 // emits w and vrow of each entry.

@@ -566,6 +566,7 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
     }
     else if (k == "overlap_auc") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->overlap_auc = (int)x; }
     else if (k == "lookup_ilp") { if (!need_int(1, 4)) { delete h; return DFB_ERR_PARAM; } g_lookup_ilp = (int)x; }
+    else if (k == "update_persistent") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } g_update_persistent = (int)x; }
     else if (k == "lookup_ctas") { if (!need_int(1, 64)) { delete h; return DFB_ERR_PARAM; } g_lookup_ctas = (int)x; }
     else if (k == "k1_tma") { if (!need_int(0, 1)) { delete h; return DFB_ERR_PARAM; } h->k1_tma = (int)x; }
     else if (k == "long_row_nnz") { if (!need_int(0, 1 << 30)) { delete h; return DFB_ERR_PARAM; } h->long_row_nnz = (int)x; }
@@ -596,6 +597,8 @@ int dfb_create(const char* const* keys, const char* const* vals, int n, dfb_hand
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
+  // (default priority: on one GPU a high-priority localizer takes SM slots from the latency-bound lookup / gather
+  // kernels of the current step and costs ~4 %, measured; the sharded store's worker stream does get priority)
   if ((e = cudaStreamCreateWithFlags(&h->loc_stream, cudaStreamNonBlocking)) != cudaSuccess) return cfail("cudaStreamCreate");
   for (auto& L : h->loc) {
     if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess) return cfail("cudaEventCreate");

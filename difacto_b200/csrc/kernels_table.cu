@@ -1068,7 +1068,7 @@ inline int grid_warps(size_t nwarps_needed, int warps_per_block, int cap) {
 }  // namespace
 
 // tuning knobs of k_lookup (engine kwargs lookup_ilp / lookup_ctas; process-wide)
-int g_lookup_ilp = 2, g_lookup_ctas = 64;
+int g_lookup_ilp = 2, g_lookup_ctas = 64, g_update_persistent = 0;
 
 int launch_table_init(Table& t, unsigned seed, cudaStream_t s) {
   k_table_init<<<148 * 8, 256, 0, s>>>(t.tab, t.cap, t.state, t.prog, seed);
@@ -1258,7 +1258,10 @@ int launch_bwd_update(Table& t, const Params& p, const int* slot, const int* pul
                                                        p_row, pxv, flags, acc_pen, nullptr, nullptr, nullptr, noseg, sa, hp)
 #define DFB_BU(K)                                                                                          \
   do {                                                                                                     \
-    const int grid = grid_warps((n + 31) / 32, 8, 148 * 8);                                                \
+    /* one short-lived CTA per 256 keys, so that the higher-priority streams working on the NEXT step (localizer;  \
+       worker / lookup streams of the sharded store) get SM slots as CTAs retire -- a grid-stride grid holds     \
+       every slot until the kernel ends (kwarg update_persistent=1 restores it, for A/B) */                    \
+    const int grid = grid_warps((n + 31) / 32, 8, (shard || !g_update_persistent) ? (1 << 22) : 148 * 8);  \
     if (shard) { if (valued) DFB_BU_(K, true, 2); else DFB_BU_(K, false, 2); }                             \
     else       { if (valued) DFB_BU_(K, true, 0); else DFB_BU_(K, false, 0); }                             \
   } while (0)

@@ -440,9 +440,14 @@ int dfb_shard_init(dfb_handle h, int rank, int nranks, size_t max_rows, size_t m
   if ((e = cudaMalloc(&sh->mailbox, sh->lay.total)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMalloc(shard mailbox)"));
   if ((e = cudaMemset(sh->mailbox, 0, sh->lay.total)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaMemset(shard mailbox)"));
   sh->peer[rank] = sh->mailbox;
-  if ((e = cudaStreamCreateWithFlags(&sh->w_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
+  // the worker stream (localize / scatter of the NEXT step) and the lookup stream run beside the owner's update of
+  // the current step on the engine's main stream: give them the higher priority, or the update's CTAs (queued
+  // first) would take every SM slot that frees up and the overlap would not happen
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if ((e = cudaStreamCreateWithPriority(&sh->w_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
   if ((e = cudaStreamCreateWithFlags(&sh->f_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
-  if ((e = cudaStreamCreateWithFlags(&sh->l_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
+  if ((e = cudaStreamCreateWithPriority(&sh->l_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(h->cuda_fail(e, "cudaStreamCreate"));
   cudaEvent_t* evs[] = {sh->ev_struct, sh->ev_part, sh->ev_reduce, sh->ev_auc, sh->ev_upd, sh->ev_fin, sh->ev_lookup};
   for (auto* ev : evs)
     for (int i = 0; i < 2; ++i)
