@@ -288,7 +288,7 @@ def test_very_hot_keys_prereduced_in_chunks_vs_oracle():
     batches = []
     for valued in (False, True, False):
         b = rand_batch(rng, 3000, 12, 25, valued, min_nnz=4)
-        b[2][b[0][:-1].astype(np.int64)] = np.uint64(77) * np.uint64(0x9E3779B97F4A7C15)     # first nnz of every row: one feature
+        b[2][b[0][:-1].astype(np.int64)] = (np.array([77], np.uint64) * np.uint64(0x9E3779B97F4A7C15))[0]     # first nnz of every row: one feature
         batches.append(b)
     M, E = run_both(kw, batches, epochs=2, val_every=0, hot_split=100)
     keys = np.unique(np.concatenate([O.reverse_bytes_np(b[2]) for b in batches]))
