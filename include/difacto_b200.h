@@ -306,7 +306,7 @@ int dfb_dev_fm_step_peer(dfb_handle h, size_t nrows, size_t nnz, const uint64_t*
 
 /* ---------------------------------------------------------------------------------
  * The NVLink-sharded store behind the C-ABI: N engines (one per GPU; one process per GPU with CUDA IPC, or
- * N threads of one process) form one model, rank r owning the r-th range of the reversed key space exactly
+ * all of them in one process with peer access) form one model, rank r owning the r-th range of the reversed key space exactly
  * like ps-lite's servers (postoffice.cc:127-136).  It replaces, for this path, the worker/server exchange of
  * the reference (SGDLearner's workers calling Store::Pull / Push on KVWorker, the servers running
  * SGDUpdater; src/sgd/sgd_learner.cc:78-89,138-177, ps-lite/include/ps/kv_app.h:406-460).
