@@ -110,8 +110,11 @@ __device__ __forceinline__ void block_add_loss(float loss_acc, size_t nrows, Dev
 #ifndef DFB_FM_PF_MAXK
 #define DFB_FM_PF_MAXK 16       // metadata prefetch (one chunk ahead) for V_dim <= this
 #endif
+#ifndef DFB_FM_MINBLOCKS32
+#define DFB_FM_MINBLOCKS32 DFB_FM_MINBLOCKS     // V_dim = 32 (tuning builds: 3 removes its ~130-byte spills)
+#endif
 template <int K, int MODE, bool HAS_VAL>
-__global__ void __launch_bounds__(256, DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, FmView v, PartArgs pa) {
+__global__ void __launch_bounds__(256, K == 32 ? DFB_FM_MINBLOCKS32 : DFB_FM_MINBLOCKS) k_fm_fast(FmBatch b, FmView v, PartArgs pa) {
   constexpr bool TRAIN = MODE == 1;
   constexpr int LPR = K / 4;                 // lanes per V row, one float4 each
   constexpr int G = 32 / LPR;                // V rows fetched by one warp-wide load
