@@ -110,20 +110,29 @@ class LibsvmPartReader {
  * fixed-size minibatches with the reference's options (src/reader/batch_reader.cc:8-78):
  * shuffle_buf_size > 0 draws the batch from a shuffled window of that many rows; neg_sampling < 1
  * drops negative rows with probability 1 - neg_sampling (rand_r, seed 0, as the reference);
- * all-ones value arrays are dropped (:71-73).  The shuffle order uses std::mt19937 instead of the
- * reference's std::random_shuffle (whose order is implementation-defined): same distribution,
- * different permutation.  Rows are streamed window by window (a shuffle window, or max(batch_size, 4096) rows):
- * the file part is never held in memory as a whole.
+ * all-ones value arrays are dropped (:71-73).  Rows are streamed window by window (a shuffle window, or
+ * max(batch_size, 4096) rows): the file part is never held in memory as a whole.
+ *
+ * Two shuffle orders:
+ *  kReference  the reference's own order on this toolchain: std::random_shuffle (batch_reader.cc:45) is, in libstdc++,
+ *              "for i in 1..n-1: swap(a[i], a[rand() % (i + 1)])" on the process-wide rand() state; the permutation
+ *              vector persists from window to window and is reset only when the window size changes (:40-44); the
+ *              down-sampling draws start from rand_r seed 0 (:16).  Every epoch sees another order because the global
+ *              generator moves on.  Checked against the compiled reference (tests/test_host_cpp.py).  rand() is not
+ *              for concurrent callers: one reader thread at a time.
+ *  kSeeded     std::mt19937 seeded by (epoch, part): another order every epoch, reproducible whatever else runs in
+ *              the process -- used where several readers parse concurrently (num_gpus > 1).
  */
+enum class ShuffleOrder { kSeeded, kReference };
+
 class BatchReader {
  public:
   BatchReader(const std::string& uri, const std::string& format, unsigned part, unsigned nparts,
               unsigned batch_size, unsigned shuffle_buf_size = 0, float neg_sampling = 1.0f, unsigned epoch = 0,
-              size_t chunk_bytes = 0)
+              size_t chunk_bytes = 0, ShuffleOrder order = ShuffleOrder::kSeeded)
       : batch_size_(batch_size), shuf_buf_(shuffle_buf_size), neg_sampling_(neg_sampling),
-        seed_(epoch * 2654435761u + part), src_(Open(uri, format, part, nparts, chunk_bytes)),
-        // the reference's std::random_shuffle advances one global generator, so every epoch sees another order;
-        // here the order is a function of (epoch, part): different per epoch, reproducible per run
+        seed_(order == ShuffleOrder::kReference ? 0u : epoch * 2654435761u + part),
+        src_(Open(uri, format, part, nparts, chunk_bytes)), mode_(order),
         gen_(epoch * 2654435761u + part * 40503u + 1u) {
     if (shuf_buf_) DFB_CHECK(shuf_buf_ >= batch_size_);
   }
@@ -161,9 +170,20 @@ class BatchReader {
     win_.Clear();
     const size_t want = shuf_buf_ ? shuf_buf_ : std::max<size_t>(batch_size_, 4096);
     while (win_.Size() < want && src_.ReadRows(&win_, want - win_.Size())) {}
-    order_.resize(win_.Size());
-    std::iota(order_.begin(), order_.end(), 0u);
-    if (shuf_buf_) std::shuffle(order_.begin(), order_.end(), gen_);
+    if (shuf_buf_ && mode_ == ShuffleOrder::kReference) {
+      if (order_.size() != win_.Size()) {
+        order_.resize(win_.Size());
+        std::iota(order_.begin(), order_.end(), 0u);
+      }
+      for (size_t i = 1; i < order_.size(); ++i) {       // libstdc++'s std::random_shuffle(first, last)
+        const size_t j = static_cast<size_t>(std::rand()) % (i + 1);
+        if (i != j) std::swap(order_[i], order_[j]);
+      }
+    } else {
+      order_.resize(win_.Size());
+      std::iota(order_.begin(), order_.end(), 0u);
+      if (shuf_buf_) std::shuffle(order_.begin(), order_.end(), gen_);
+    }
     cursor_ = 0;
     return !order_.empty();
   }
@@ -171,6 +191,7 @@ class BatchReader {
   float neg_sampling_;
   unsigned int seed_;
   LibsvmPartReader src_;
+  ShuffleOrder mode_;
   std::mt19937 gen_;
   RowBlockContainer<feaid_t> win_, batch_;
   std::vector<unsigned> order_;

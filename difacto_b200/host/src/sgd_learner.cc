@@ -341,7 +341,8 @@ void SGDLearner::IterateData(const sgd::Job& job, sgd::Progress* progress) {
                      static_cast<unsigned>(job.part_idx), static_cast<unsigned>(job.num_parts),
                      train ? static_cast<unsigned>(param_.batch_size) : 65536u,
                      train ? static_cast<unsigned>(param_.batch_size) * static_cast<unsigned>(param_.shuffle) : 0u,
-                     train ? param_.neg_sampling : 1.0f, static_cast<unsigned>(job.epoch));
+                     train ? param_.neg_sampling : 1.0f, static_cast<unsigned>(job.epoch), 0,
+                     ShuffleOrder::kReference);      // one reader at a time: the reference's own shuffle order
   while (reader.Next()) {
     const bool push_cnt = train && job.epoch == 0;   // :201-202
     if (param_.fused == 1) {

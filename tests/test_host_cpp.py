@@ -41,6 +41,52 @@ def test_host_unit_cases_cpu(host_bin, libsvm_fixture):
     assert "BatchReader.StreamedChunks" in out.stdout
 
 
+_REF_BATCH = r"""
+import sys
+sys.path.insert(0, sys.argv[1])
+from oracle import oracle as O
+path, part, nparts, bs, shuf, neg, which = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), float(sys.argv[7]), int(sys.argv[8])
+r = O.ref_read_batch(path, "libsvm", part, nparts, bs, shuf, neg, which)
+if r is None:
+    print("END")
+else:
+    off, lab, idx, val = r
+    hi = hl = 0
+    for x in idx.tolist():
+        hi = (hi * 1000003 + x) & 0xFFFFFFFFFFFFFFFF
+    for y in lab.tolist():
+        hl = (hl * 1000003 + (1 if y > 0 else 2)) & 0xFFFFFFFFFFFFFFFF
+    print(which, len(lab), len(idx), hi, hl, 1 if val is not None else 0)
+"""
+
+
+@pytest.mark.parametrize("part,nparts,bs,shuf,neg,nb", [(0, 1, 10, 30, 1.0, 5), (1, 2, 7, 21, 0.5, 4)])
+def test_shuffled_batches_equal_the_reference_reader(host_bin, libsvm_fixture, part, nparts, bs, shuf, neg, nb):
+    """shuffle window + negative down-sampling: the host BatchReader in its reference order (libstdc++'s
+    std::random_shuffle on rand(), persistent permutation, rand_r seed 0: src/reader/batch_reader.cc:8-78) yields the
+    very batches of the reference's BatchReader, row for row.  rand() is process-wide state, so every batch of the
+    compiled reference (oracle/_ref) is read in a fresh interpreter that replays the reader from the start."""
+    from oracle import oracle as O
+    if not O.have_ref():
+        pytest.skip("the compiled reference (oracle/_ref) is not available")
+    ours = subprocess.run([os.path.join(host_bin, "batch_dump"), libsvm_fixture, str(part), str(nparts), str(bs), str(shuf),
+                           str(neg), str(nb), "reference"], capture_output=True, text=True)
+    assert ours.returncode == 0, ours.stderr
+    ref = []
+    for b in range(nb):
+        out = subprocess.run([sys.executable, "-c", _REF_BATCH, ROOT, libsvm_fixture, str(part), str(nparts), str(bs), str(shuf),
+                              str(neg), str(b)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        ref.append(out.stdout.strip().split("\n")[-1])
+    ref = [r for r in ref if r != "END"]
+    assert len(ref) >= 3
+    assert ours.stdout.strip().split("\n") == ref
+    # the seeded order (num_gpus > 1: concurrent readers) is a different permutation of the same rows
+    seeded = subprocess.run([os.path.join(host_bin, "batch_dump"), libsvm_fixture, str(part), str(nparts), str(bs), str(shuf),
+                             "1.0", str(nb), "seeded"], capture_output=True, text=True)
+    assert seeded.returncode == 0 and len(seeded.stdout.strip().split("\n")) == nb
+
+
 def test_cli_conf_surface(host_bin, tmp_path, libsvm_fixture):
     conf = tmp_path / "sgd.conf"
     conf.write_text(f"# data\ndata_in = {libsvm_fixture}\nl1 = 1\nlr = .1\nlearner = sgd\n"
