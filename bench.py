@@ -44,8 +44,8 @@ def parse_args():
     ap.add_argument("--nnz", type=int, default=100)
     ap.add_argument("--vdim", type=int, default=64)
     ap.add_argument("--id-space", type=int, default=10 ** 9)
-    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "criteo39", "gisette"])
-    ap.add_argument("--hyper", default="allV", choices=["allV", "criteo_conf", "ftrl_l1"])
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "criteo39", "gisette", "rcv1"])
+    ap.add_argument("--hyper", default="allV", choices=["allV", "criteo_conf", "ftrl_l1", "rcv1_conf"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the short runs of the other named configs")
     ap.add_argument("--cold", action="store_true", help="cold table: every timed batch brings only new keys")
     ap.add_argument("--working-set", type=int, default=8, help="distinct batches cycled (per rank)")
@@ -72,10 +72,11 @@ def reverse_bytes_np(x):
 
 
 GISETTE_NNZ = 5000      # gisette: 5000 dense features per example (the "long row" shape)
+RCV1_NNZ, RCV1_IDS = 74, 47236      # rcv1.binary: ~74 tf-idf features per document out of 47236
 
 
 def nnz_of(args):
-    return {"synthetic": args.nnz, "criteo39": 39, "gisette": GISETTE_NNZ}[args.workload]
+    return {"synthetic": args.nnz, "criteo39": 39, "gisette": GISETTE_NNZ, "rcv1": RCV1_NNZ}[args.workload]
 
 
 def gen_raw_batch(args, seed, rows=None):
@@ -89,6 +90,13 @@ def gen_raw_batch(args, seed, rows=None):
         off = (np.arange(B + 1, dtype=np.uint64) * np.uint64(nnz))
         lab = np.where(rng.random(B) < 0.5, 1.0, -1.0).astype(np.float32)
         return off, lab, ids, (rng.random(B * nnz, dtype=np.float32) * np.float32(0.02))
+    if args.workload == "rcv1":
+        # BASELINE.json configs[1] stand-in: 74 real-valued (tf-idf-like, U(0, 0.3)) features per row, ids over 47236
+        nnz = RCV1_NNZ
+        ids = rng.integers(1, RCV1_IDS + 1, B * nnz).astype(np.uint64)
+        off = (np.arange(B + 1, dtype=np.uint64) * np.uint64(nnz))
+        lab = np.where(rng.random(B) < 0.5, 1.0, -1.0).astype(np.float32)
+        return off, lab, ids, (rng.random(B * nnz, dtype=np.float32) * np.float32(0.3))
     if args.workload == "criteo39":
         # 13 "integer" + 26 "categorical" groups, id = (hash << 12) | group (criteo_parser.h:68-88), Zipf-ish hashes
         nnz = 39
@@ -115,13 +123,16 @@ def hyper(args):
     """hyper-parameters by --hyper (other values are the defaults of src/sgd/sgd_param.h:94-106):
        allV         V_threshold=0, l1=0: every key owns a V row (the bandwidth worst case of SURVEY.md 8d, config S)
        criteo_conf  the regularisation of example/criteo_sgd.conf:10-17 (l1=l2=V_l2=10, V_threshold=10)
-       ftrl_l1      the defaults (l1=1, V_threshold=10): l1-regularised FTRL, most keys have w == 0 and therefore no V"""
+       ftrl_l1      the defaults (l1=1, V_threshold=10): l1-regularised FTRL, most keys have w == 0 and therefore no V
+       rcv1_conf    example/rcv1_sgd.conf (l1=1, lr=.1), the other values at their defaults"""
     base = dict(V_dim=args.vdim, l1=0.0, l2=0.0, lr=0.01, lr_beta=1.0, V_l2=0.01, V_lr=0.01, V_lr_beta=1.0,
                 V_init_scale=0.01, V_threshold=0, seed=0)
     if args.hyper == "criteo_conf":
         base.update(l1=10.0, l2=10.0, V_l2=10.0, V_threshold=10)
     elif args.hyper == "ftrl_l1":
         base.update(l1=1.0, l2=0.0, V_threshold=10)
+    elif args.hyper == "rcv1_conf":        # example/rcv1_sgd.conf: l1 = 1, lr = .1 (+ V_dim given on the command line)
+        base.update(l1=1.0, lr=0.1, V_threshold=10)
     return base
 
 
@@ -252,6 +263,8 @@ def workload_config(args, extra):
                         if args.workload == "synthetic" else
                         f"gisette-shaped CSR: batch {args.batch} x {GISETTE_NNZ} dense real-valued features, V_dim={args.vdim}, "
                         f"hyper={args.hyper}" if args.workload == "gisette" else
+                        f"rcv1-shaped CSR (BASELINE.json configs[1] stand-in): batch {args.batch} x {RCV1_NNZ} real-valued nnz/row over "
+                        f"{RCV1_IDS} ids, V_dim={args.vdim}, hyper={args.hyper}" if args.workload == "rcv1" else
                         f"criteo-shaped CSR: batch {args.batch} x 39 nnz/row, Zipf ids with 12-bit group id, "
                         f"V_dim={args.vdim}, hyper={args.hyper}"),
            "global_batch": args.batch * args.gpus, "batch_per_gpu": args.batch, "nnz_per_row": nnz, "V_dim": args.vdim,
@@ -338,7 +351,7 @@ def run_single(args, local_rank, full, sampler=None):
         localizer_check = bool(np.array_equal(gl, nl) and np.array_equal(gk, nk) and np.array_equal(gc, nc))
     probe.close()
     cap = int(nb * U0 * 1.05) + 4096
-    id_bits = int(np.ceil(np.log2(float(max(args.id_space * (nb if cold else 1), 2))))) if args.workload == "synthetic" else (13 if args.workload == "gisette" else 64)
+    id_bits = int(np.ceil(np.log2(float(max(args.id_space * (nb if cold else 1), 2))))) if args.workload == "synthetic" else {"gisette": 13, "rcv1": 16}.get(args.workload, 64)
     E = capi.Engine(device=local_rank, table_capacity=cap, V_capacity=cap, id_bits=min(id_bits, 64),
                     overlap_auc=0 if args.no_overlap_auc else 1, **extra, **kw)
     devb = [dict(off=h["off"].to(dev), lab=h["lab"].to(dev), ids=h["ids"].to(dev),
@@ -475,7 +488,11 @@ def sweep_configs(args):
             # long rows: 1024 examples x 5000 dense features (5.1 M nnz per step); CTA-per-row forward vs warp-per-row
             ("gisette_V64_long_rows", cfg(workload="gisette", batch=1024, vdim=64)),
             ("gisette_V64_warp_per_row", cfg(workload="gisette", batch=1024, vdim=64,
-                                             engine_kw=",".join(x for x in (args.engine_kw, "long_row_nnz=0") if x)))]
+                                             engine_kw=",".join(x for x in (args.engine_kw, "long_row_nnz=0") if x))),
+            # BASELINE.json configs[1]: rcv1_sgd.conf + V_dim=16 (74 real-valued nnz per row over 47236 ids: every key is
+            # hot); at the batch this bench uses and at the conf's own batch_size = 100 (launch-bound)
+            ("rcv1_V16_conf_batch65536", cfg(workload="rcv1", vdim=16, hyper="rcv1_conf")),
+            ("rcv1_V16_conf_batch100", cfg(workload="rcv1", vdim=16, hyper="rcv1_conf", batch=100, steps=20))]
 
 
 def main_b200(args, rank, world, local_rank):
